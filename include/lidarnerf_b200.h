@@ -1,0 +1,212 @@
+/*
+ * lidarnerf_b200.h - C ABI of the B200-native LiDAR-NeRF volume-rendering hot path.
+ *
+ * One entry point per function the reference binds through pybind11 for this path
+ * (boundary B1).  Every entry point takes plain device pointers and
+ * sizes - no torch types - plus the CUDA stream to launch on, is asynchronous (no host
+ * sync), allocates nothing and returns an int status:
+ *      0                       success
+ *      > 0                     a cudaError_t raised by the launch
+ *      LNB_ERR_* (negative)    argument / configuration rejected before any launch
+ * All outputs are pre-allocated by the caller and written in place, exactly like the
+ * reference's `_backend.*` functions.  `lnb_strerror` turns a status into text.
+ *
+ * Citations are relative to the reference checkout (tangtaogo/lidar-nerf).
+ */
+#ifndef LIDARNERF_B200_H_
+#define LIDARNERF_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef void *lnb_stream_t; /* a cudaStream_t; NULL = legacy default stream */
+
+#define LNB_OK 0
+#define LNB_ERR_INVALID_ARGUMENT (-1) /* NULL pointer, zero size where not allowed, bad enum */
+#define LNB_ERR_UNSUPPORTED (-2)      /* shape / dtype outside what this build implements     */
+#define LNB_ERR_NO_DEVICE (-3)        /* no sm_100 device / CUDA runtime unavailable           */
+#define LNB_ERR_WORKSPACE (-4)        /* caller-provided workspace too small                    */
+
+/* element types for the gridencoder tables (reference dispatches on embeddings.scalar_type()) */
+#define LNB_F32 0
+#define LNB_F16 1
+
+/* memory layout of the per-level feature tensor */
+#define LNB_LAYOUT_LBC 0 /* [L, B, C]   - what the reference kernels read/write (gridencoder.cu:117,287) */
+#define LNB_LAYOUT_BLC 1 /* [B, L * C]  - what the MLP consumes; saves the torch permute (grid.py:87,104)   */
+
+const char *lnb_strerror(int status);
+/* library version (major*10000 + minor*100 + patch) and the arch it was compiled for ("sm_100a") */
+int lnb_version(void);
+const char *lnb_arch(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t lnb_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------
+ * raymarching  (replaces lidarnerf/raymarching/src/raymarching.h:6-96, bindings.cpp:5-21)
+ * All floating tensors are fp32 (the reference wrappers cast to float32:
+ * raymarching.py:17,53,138,173,294,369,465).
+ * ---------------------------------------------------------------------------------------- */
+
+/* raymarching.cu:159-177  rays_o/rays_d [N,3], aabb [6] -> nears/fars [N] */
+int lnb_near_far_from_aabb(const float *rays_o, const float *rays_d, const float *aabb, uint32_t N,
+                           float min_near, float *nears, float *fars, lnb_stream_t stream);
+
+/* raymarching.cu:219-233  -> coords [N,2] in [-1,1] */
+int lnb_sph_from_ray(const float *rays_o, const float *rays_d, float radius, uint32_t N,
+                     float *coords, lnb_stream_t stream);
+
+/* raymarching.cu:249-253 / 274-280  coords [N,3] int32 <-> indices [N] int32 */
+int lnb_morton3D(const int32_t *coords, uint32_t N, int32_t *indices, lnb_stream_t stream);
+int lnb_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, lnb_stream_t stream);
+
+/* raymarching.cu:308-320  grid [N*8] fp32 -> bitfield [N] u8, bit i = grid[8n+i] > thresh */
+int lnb_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield,
+                 lnb_stream_t stream);
+
+/* raymarching.cu:536-568.  counter[0] += samples, counter[1] += rays (device atomics);
+ * rays [N,3] = (ray id, sample offset, sample count) in arrival order; samples of a ray whose
+ * span would exceed M are not written (raymarching.cu:456-457). */
+int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                         float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                         uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
+                         float *deltas, int32_t *rays, int32_t *counter, const float *noises,
+                         lnb_stream_t stream);
+
+/* raymarching.cu:657-678.  rgbs [M,3]; outputs indexed by rays[n,0]. */
+int lnb_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas,
+                                     const int32_t *rays, uint32_t M, uint32_t N, float T_thresh,
+                                     float *weights_sum, float *depth, float *image,
+                                     lnb_stream_t stream);
+
+/* raymarching.cu:774-802.  grad_sigmas/grad_rgbs must be zero-filled by the caller
+ * (raymarching.py:338-339); there is no depth gradient (raymarching.py:329-330). */
+int lnb_composite_rays_train_backward(const float *grad_weights_sum, const float *grad_image,
+                                      const float *sigmas, const float *rgbs, const float *deltas,
+                                      const int32_t *rays, const float *weights_sum,
+                                      const float *image, uint32_t M, uint32_t N, float T_thresh,
+                                      float *grad_sigmas, float *grad_rgbs, lnb_stream_t stream);
+
+/* Extension used by this repo's run_cuda glue: `channels` in {1,2,3,4}
+ * (the LiDAR head emits 2: ray-drop, intensity); optional depth gradient (`grad_depth` and
+ * `depth` may both be NULL = reference behaviour).  With channels == 3 and grad_depth == NULL
+ * these are the two functions above. */
+int lnb_composite_rays_train_forward_ex(const float *sigmas, const float *rgbs, const float *deltas,
+                                        const int32_t *rays, uint32_t M, uint32_t N, float T_thresh,
+                                        uint32_t channels, float *weights_sum, float *depth,
+                                        float *image, lnb_stream_t stream);
+int lnb_composite_rays_train_backward_ex(const float *grad_weights_sum, const float *grad_depth,
+                                         const float *grad_image, const float *sigmas,
+                                         const float *rgbs, const float *deltas, const int32_t *rays,
+                                         const float *weights_sum, const float *depth,
+                                         const float *image, uint32_t M, uint32_t N, float T_thresh,
+                                         uint32_t channels, float *grad_sigmas, float *grad_rgbs,
+                                         lnb_stream_t stream);
+
+/* raymarching.cu:930-964 (inference march; xyzs/dirs/deltas zero-filled by the caller) */
+int lnb_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
+                   const float *rays_o, const float *rays_d, float bound, float dt_gamma,
+                   uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid,
+                   const float *nears, const float *fars, float *xyzs, float *dirs, float *deltas,
+                   const float *noises, lnb_stream_t stream);
+
+/* raymarching.cu:1055-1077 (inference composite, in place; rays_alive[n] = -1 on termination) */
+int lnb_composite_rays(uint32_t n_alive, uint32_t n_step, float T_thresh, int32_t *rays_alive,
+                       float *rays_t, const float *sigmas, const float *rgbs, const float *deltas,
+                       float *weights_sum, float *depth, float *image, lnb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * gridencoder  (replaces lidarnerf/gridencoder/src/gridencoder.h:12-55, bindings.cpp:5-11)
+ * inputs are always fp32 in [0,1] (gridencoder.cu:96,629); `dtype` is the type of embeddings,
+ * outputs, dy_dx, grad, grad_embeddings and grad_inputs (LNB_F32 / LNB_F16).
+ * D in {2,3}; C in {1,2,4,8}.  S = log2(per_level_scale); H = base resolution.
+ * ---------------------------------------------------------------------------------------- */
+
+/* gridencoder.cu:594-637.  dy_dx [B, L*D*C] may be NULL.  layout selects the outputs layout. */
+int lnb_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets,
+                            void *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                            uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners,
+                            uint32_t interp, int dtype, int layout, lnb_stream_t stream);
+
+/* gridencoder.cu:639-693.  grad_embeddings (and grad_inputs when dy_dx != NULL) must be
+ * zero-filled by the caller (grid.py:106-109); gradients are accumulated with atomics. */
+int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings,
+                             const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx,
+                             void *grad_inputs, uint32_t gridtype, int align_corners,
+                             uint32_t interp, int dtype, int layout, lnb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * freqencoder  (replaces lidarnerf/freqencoder/src/freqencoder.h, bindings.cpp:5-9)   fp32
+ * ---------------------------------------------------------------------------------------- */
+int lnb_freq_encode_forward(const float *inputs, uint32_t B, uint32_t D, uint32_t deg, uint32_t C,
+                            float *outputs, lnb_stream_t stream);
+int lnb_freq_encode_backward(const float *grad, const float *outputs, uint32_t B, uint32_t D,
+                             uint32_t deg, uint32_t C, float *grad_inputs, lnb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * shencoder  (replaces lidarnerf/shencoder/src/shencoder.h, bindings.cpp:5-8)   fp32, D == 3,
+ * C = degree in [1,8]; outputs [B, C*C]; dy_dx [B, 3*C*C] may be NULL.
+ * ---------------------------------------------------------------------------------------- */
+int lnb_sh_encode_forward(const float *inputs, float *outputs, uint32_t B, uint32_t D, uint32_t C,
+                          float *dy_dx, lnb_stream_t stream);
+int lnb_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, uint32_t D, uint32_t C,
+                           const float *dy_dx, float *grad_inputs, lnb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * ffmlp  (replaces lidarnerf/ffmlp/src/ffmlp.h:7-47, bindings.cpp:5-10)
+ * fp16 storage, bias-free:  h0 = act(x W_in^T), h_k = act(h_{k-1} W_k^T), y = h_last W_out^T.
+ * weights = [hidden*in | (num_layers-1)*hidden*hidden | out*hidden] row-major fp16
+ * (ffmlp.cu:861-864).  B must be a multiple of 128 (ffmlp.py:254-262 pads).  This build
+ * implements hidden_dim == 64, input_dim % 16 == 0 (<= 128), output_dim == 16, activation ReLU
+ * (0) and output activation None (6); anything else returns LNB_ERR_UNSUPPORTED.
+ * Accumulation is fp32 in tensor memory (a superset of the reference's fp16 accumulators).
+ * forward_buffer / backward_buffer: [num_layers, B, hidden] fp16 (post-activation / d(pre-act)).
+ * ---------------------------------------------------------------------------------------- */
+int lnb_ffmlp_forward(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                      uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                      uint32_t activation, uint32_t output_activation, void *forward_buffer,
+                      void *outputs, lnb_stream_t stream);
+int lnb_ffmlp_inference(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                        uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                        uint32_t activation, uint32_t output_activation, void *inference_buffer,
+                        void *outputs, lnb_stream_t stream);
+/* grad_weights (fp16, zero-filled by the caller, ffmlp.py:124) receives the weight gradient;
+ * grad_inputs [B,in] is written when calc_grad_inputs != 0.  `workspace` must hold
+ * lnb_ffmlp_backward_workspace_bytes(...) bytes of device memory (fp32 weight-gradient
+ * accumulators); it is zeroed and consumed inside the call. */
+size_t lnb_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_dim,
+                                          uint32_t hidden_dim, uint32_t num_layers);
+int lnb_ffmlp_backward(const void *grad, const void *inputs, const void *weights,
+                       const void *forward_buffer, uint32_t B, uint32_t input_dim,
+                       uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                       uint32_t activation, uint32_t output_activation, int calc_grad_inputs,
+                       void *backward_buffer, void *grad_inputs, void *grad_weights,
+                       void *workspace, size_t workspace_bytes, lnb_stream_t stream);
+/* ffmlp.cu:1030-1049 create/destroy split-K side streams.  This implementation accumulates the
+ * weight gradient in tensor memory inside the backward kernel and needs no side streams; the
+ * two symbols are kept so the reference's FFMLP.__init__ (ffmlp.py:230) binds unchanged. */
+int lnb_allocate_splitk(size_t size);
+int lnb_free_splitk(void);
+
+/* ------------------------------------------------------------------------------------------
+ * Training-step helpers that the reference leaves to torch.
+ * ---------------------------------------------------------------------------------------- */
+
+/* Fused Adam over a flat fp32 parameter vector with fp32 gradients:
+ *   g = grad * grad_scale;  m = b1 m + (1-b1) g;  v = b2 v + (1-b2) g^2;
+ *   p -= lr * (m / bc1) / (sqrt(v / bc2) + eps)          (torch.optim.Adam semantics)
+ * If `params_half` != NULL the updated parameters are also written as fp16 (the table the
+ * encoders read); if `zero_grad` != 0 the gradient is cleared in the same pass. */
+int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half,
+                  size_t n, float lr, float beta1, float beta2, float eps, float bias_correction1,
+                  float bias_correction2, float grad_scale, int zero_grad, lnb_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDARNERF_B200_H_ */

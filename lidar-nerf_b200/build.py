@@ -1,0 +1,75 @@
+"""Build liblnb200.so (the C-ABI CUDA library of include/lidarnerf_b200.h) in-tree with nvcc for sm_100a.
+
+    python lidar-nerf_b200/build.py [--force] [--verbose]
+
+One translation unit per reference extension (csrc/*.cu), compiled in parallel with
+`-gencode arch=compute_100a,code=sm_100a -lineinfo`, linked into lidar-nerf_b200/lib/liblnb200.so.
+The .so is git-ignored but travels to the GPU box with the gpurun snapshot.
+"""
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB_DIR = os.path.join(HERE, "lib")
+OBJ_DIR = os.path.join(HERE, "build")
+LIB = os.path.join(LIB_DIR, "liblnb200.so")
+UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "optim", "fused"]
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def _nvcc():
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found; lidar-nerf_b200 has no CPU fallback and cannot be built without CUDA")
+
+
+def _newest_header():
+    hs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
+    hs.append(os.path.join(HERE, "..", "include", "lidarnerf_b200.h"))
+    return max(os.path.getmtime(h) for h in hs)
+
+
+def build(force=False, verbose=False):
+    nvcc = _nvcc()
+    os.makedirs(LIB_DIR, exist_ok=True)
+    os.makedirs(OBJ_DIR, exist_ok=True)
+    hdr = _newest_header()
+    units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u + ".cu"))]
+    todo = []
+    for u in units:
+        src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(OBJ_DIR, u + ".o")
+        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr):
+            todo.append((u, src, obj))
+
+    def compile_one(item):
+        u, src, obj = item
+        cmd = [nvcc, *ARCH, *FLAGS, "-c", src, "-o", obj]
+        if verbose:
+            cmd.insert(1, "-Xptxas=-v")
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        return u, r
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=min(len(todo), os.cpu_count() or 4)) as ex:
+            for u, r in ex.map(compile_one, todo):
+                if verbose or r.returncode != 0:
+                    sys.stderr.write(f"--- nvcc {u} ---\n{r.stdout}{r.stderr}\n")
+                if r.returncode != 0:
+                    raise RuntimeError(f"nvcc failed on csrc/{u}.cu")
+    objs = [os.path.join(OBJ_DIR, u + ".o") for u in units]
+    if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
+        r = subprocess.run([nvcc, "-shared", *ARCH, "-o", LIB, *objs], capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(r.stdout + r.stderr)
+            raise RuntimeError("link of liblnb200.so failed")
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))

@@ -1,0 +1,455 @@
+// Multiresolution hash / tiled grid encoding for sm_100a.
+//
+// Behavioural spec: lidarnerf/gridencoder/src/gridencoder.cu of the reference
+//   index/hash      :53-93      forward  :95-263      backward :265-362     input grad :364-390
+// Design: a CTA owns a tile of 128 samples and ALL levels.  Warp w walks levels w, w+W, ... so the
+// 32 lanes of a gather instruction always hit the SAME level with 32 neighbouring samples (few
+// distinct sectors on the dense coarse levels, maximal memory-level parallelism - 8 corner loads
+// x 4 sample groups in flight per thread - on the hashed fine levels, whose 2-4 MiB tables live
+// in B200's 126 MB L2).  Results are staged through a padded shared-memory tile and leave the SM
+// as full coalesced rows, in either the reference's [L,B,C] layout or the [B,L*C] layout the MLP
+// consumes (which removes the torch permute + copy the reference pays, grid.py:87,104).
+#include "common.cuh"
+
+namespace lnb {
+namespace {
+
+constexpr int kTileB = 128;     // samples per CTA
+constexpr int kFwdThreads = 512;
+constexpr int kBwdThreads = 256;
+
+template <typename T> struct Num;
+template <> struct Num<float> {
+    static __device__ __forceinline__ float to_f(float v) { return v; }
+    static __device__ __forceinline__ float from_f(float v) { return v; }
+};
+template <> struct Num<__half> {
+    static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+    static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+};
+
+struct LevelGeo {
+    float scale;
+    uint32_t resolution, hashmap_size, table_offset;
+};
+
+// gridencoder.cu:146-148
+__device__ __forceinline__ LevelGeo level_geo(const int32_t *__restrict__ offsets, uint32_t level,
+                                              float S, uint32_t H) {
+    LevelGeo g;
+    g.table_offset = (uint32_t)offsets[level];
+    g.hashmap_size = (uint32_t)offsets[level + 1] - g.table_offset;
+    g.scale = exp2f(level * S) * H - 1.0f;
+    g.resolution = (uint32_t)ceilf(g.scale) + 1;
+    return g;
+}
+
+// gridencoder.cu:53-93: dense (strided) index while the level fits, xor-prime hash otherwise.
+template <uint32_t D>
+__device__ __forceinline__ uint32_t cell_row(const uint32_t (&p)[D], uint32_t gridtype,
+                                             bool align_corners, const LevelGeo &g) {
+    constexpr uint32_t kPrimes[7] = {1u, 2654435761u, 805459861u, 3674653429u,
+                                     2097192037u, 1434869437u, 2165219737u};
+    const uint32_t side = align_corners ? g.resolution : (g.resolution + 1);
+    uint32_t stride = 1, index = 0;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        if (stride <= g.hashmap_size) {
+            index += p[d] * stride;
+            stride *= side;
+        }
+    }
+    if (gridtype == 0 && stride > g.hashmap_size) {
+        index = 0;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) index ^= p[d] * kPrimes[d];
+    }
+    return index % g.hashmap_size;
+}
+
+template <uint32_t D>
+struct Cell {
+    uint32_t base[D];
+    float frac[D];    // interpolation weight along each axis (after optional smoothstep)
+    float dfrac[D];   // its derivative w.r.t. the fractional position
+    bool inside;
+};
+
+// gridencoder.cu:119-167
+template <uint32_t D>
+__device__ __forceinline__ Cell<D> locate(const float *__restrict__ x, const LevelGeo &g,
+                                          bool align_corners, uint32_t interp) {
+    Cell<D> c;
+    c.inside = true;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        const float v = x[d];
+        if (v < 0 || v > 1) c.inside = false;
+        float pos = v * g.scale + (align_corners ? 0.0f : 0.5f);
+        const float fl = floorf(pos);
+        c.base[d] = (uint32_t)fl;
+        pos -= (float)c.base[d];
+        if (interp == 1) {
+            c.dfrac[d] = 6 * pos * (1.0f - pos);
+            c.frac[d] = pos * pos * (3.0f - 2.0f * pos);
+        } else {
+            c.dfrac[d] = 1.0f;
+            c.frac[d] = pos;
+        }
+    }
+    return c;
+}
+
+template <typename T, uint32_t C>
+__device__ __forceinline__ void load_row(const T *__restrict__ p, float (&v)[C]) {
+    if constexpr (sizeof(T) == 2 && C % 2 == 0) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; c += 2) {
+            const __half2 h = __ldg(reinterpret_cast<const __half2 *>(p + c));
+            v[c] = __low2float(h);
+            v[c + 1] = __high2float(h);
+        }
+    } else if constexpr (sizeof(T) == 4 && C % 2 == 0) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; c += 2) {
+            const float2 f = __ldg(reinterpret_cast<const float2 *>(p + c));
+            v[c] = f.x;
+            v[c + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) v[c] = Num<T>::to_f(__ldg(p + c));
+    }
+}
+
+// Forward.  Accumulates in the table's type exactly like the reference (`scalar_t results[C]`,
+// gridencoder.cu:173-199): every `+= w * grid[...]` is rounded to T.
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(kFwdThreads)
+k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
+           const int32_t *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
+           float S, uint32_t H, T *__restrict__ dy_dx, uint32_t gridtype, bool align_corners,
+           uint32_t interp, int layout) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T *tile = reinterpret_cast<T *>(smem_raw);  // [kTileB][pitch], only for LNB_LAYOUT_BLC
+    const uint32_t F = L * C;
+    const uint32_t pitch = F + (sizeof(T) == 2 ? 2 : 1);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+    const uint32_t b0 = blockIdx.x * kTileB;
+
+    for (uint32_t level = warp; level < L; level += n_warps) {
+        const LevelGeo g = level_geo(offsets, level, S, H);
+        const T *__restrict__ tab = table + (size_t)g.table_offset * C;
+#pragma unroll
+        for (uint32_t grp = 0; grp < kTileB / 32; ++grp) {
+            const uint32_t sl = grp * 32 + lane;
+            const uint32_t b = b0 + sl;
+            if (b >= B) continue;
+            const Cell<D> cell = locate<D>(inputs + (size_t)b * D, g, align_corners, interp);
+
+            T res[C];
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) res[c] = Num<T>::from_f(0.f);
+
+            if (cell.inside) {
+#pragma unroll
+                for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+                    float w = 1;
+                    uint32_t p[D];
+#pragma unroll
+                    for (uint32_t d = 0; d < D; ++d) {
+                        if ((corner & (1u << d)) == 0) {
+                            w *= 1 - cell.frac[d];
+                            p[d] = cell.base[d];
+                        } else {
+                            w *= cell.frac[d];
+                            p[d] = cell.base[d] + 1;
+                        }
+                    }
+                    const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
+                    float v[C];
+                    load_row<T, C>(tab + (size_t)row * C, v);
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c)
+                        res[c] = Num<T>::from_f(Num<T>::to_f(res[c]) + w * v[c]);
+                }
+            }
+
+            if (layout == LNB_LAYOUT_LBC) {
+                T *o = outputs + ((size_t)level * B + b) * C;
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) o[c] = res[c];
+            } else {
+                T *o = tile + (size_t)sl * pitch + level * C;
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) o[c] = res[c];
+            }
+
+            if (dy_dx) {  // gridencoder.cu:214-262, layout [B, L, D, C]
+                T *dd = dy_dx + ((size_t)b * L + level) * D * C;
+#pragma unroll
+                for (uint32_t gd = 0; gd < D; ++gd) {
+                    T acc[C];
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) acc[c] = Num<T>::from_f(0.f);
+                    if (cell.inside) {
+#pragma unroll
+                        for (uint32_t corner = 0; corner < (1u << (D - 1)); ++corner) {
+                            float w = g.scale;
+                            uint32_t p[D];
+#pragma unroll
+                            for (uint32_t nd = 0; nd < D - 1; ++nd) {
+                                const uint32_t d = (nd >= gd) ? (nd + 1) : nd;
+                                if ((corner & (1u << nd)) == 0) {
+                                    w *= 1 - cell.frac[d];
+                                    p[d] = cell.base[d];
+                                } else {
+                                    w *= cell.frac[d];
+                                    p[d] = cell.base[d] + 1;
+                                }
+                            }
+                            p[gd] = cell.base[gd];
+                            const uint32_t r0 = cell_row<D>(p, gridtype, align_corners, g);
+                            p[gd] = cell.base[gd] + 1;
+                            const uint32_t r1 = cell_row<D>(p, gridtype, align_corners, g);
+                            float v0[C], v1[C];
+                            load_row<T, C>(tab + (size_t)r0 * C, v0);
+                            load_row<T, C>(tab + (size_t)r1 * C, v1);
+#pragma unroll
+                            for (uint32_t c = 0; c < C; ++c) {
+                                // reference: w * (right - left) * pos_deriv with (right-left) in T
+                                const float diff = Num<T>::to_f(Num<T>::from_f(v1[c] - v0[c]));
+                                acc[c] = Num<T>::from_f(Num<T>::to_f(acc[c]) + w * diff * cell.dfrac[gd]);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) dd[gd * C + c] = acc[c];
+                }
+            }
+        }
+    }
+
+    if (layout == LNB_LAYOUT_BLC) {
+        __syncthreads();
+        const uint32_t rows = min((uint32_t)kTileB, B - b0);
+        T *out = outputs + (size_t)b0 * F;
+        if ((F * sizeof(T)) % 4 == 0) {  // move 4-byte words
+            const uint32_t wpr = F * sizeof(T) / 4;
+            const uint32_t *tw = reinterpret_cast<const uint32_t *>(tile);
+            uint32_t *ow = reinterpret_cast<uint32_t *>(out);
+            const uint32_t pitch_w = pitch * sizeof(T) / 4;
+            for (uint32_t i = threadIdx.x; i < rows * wpr; i += blockDim.x) {
+                const uint32_t r = i / wpr, j = i - r * wpr;
+                ow[i] = tw[r * pitch_w + j];
+            }
+        } else {
+            for (uint32_t i = threadIdx.x; i < rows * F; i += blockDim.x) {
+                const uint32_t r = i / F, j = i - r * F;
+                out[i] = tile[r * pitch + j];
+            }
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void atomic_add_pair(T *p, float a, float b);
+template <>
+__device__ __forceinline__ void atomic_add_pair<__half>(__half *p, float a, float b) {
+    // gridencoder.cu:346-353: each contribution is rounded to half, then added with a half2 atomic
+    atomicAdd(reinterpret_cast<__half2 *>(p), __halves2half2(__float2half_rn(a), __float2half_rn(b)));
+}
+template <>
+__device__ __forceinline__ void atomic_add_pair<float>(float *p, float a, float b) {
+    atomicAdd(reinterpret_cast<float2 *>(p), make_float2(a, b));
+}
+__device__ __forceinline__ void atomic_add_one(__half *p, float a) { atomicAdd(p, __float2half_rn(a)); }
+__device__ __forceinline__ void atomic_add_one(float *p, float a) { atomicAdd(p, a); }
+
+// Backward: scatter-add of w * grad into the table gradient (gridencoder.cu:265-362).
+// grid = (ceil(B / kBwdThreads), L); one thread per (sample, level), all C channels.
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(kBwdThreads)
+k_grid_bwd(const T *__restrict__ grad, const float *__restrict__ inputs,
+           const int32_t *__restrict__ offsets, T *__restrict__ grad_table, uint32_t B, uint32_t L,
+           float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const LevelGeo g = level_geo(offsets, level, S, H);
+    const Cell<D> cell = locate<D>(inputs + (size_t)b * D, g, align_corners, interp);
+    if (!cell.inside) return;
+
+    const T *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * C
+                                             : grad + ((size_t)b * L + level) * C;
+    float gv[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) gv[c] = Num<T>::to_f(gp[c]);
+
+    T *gt = grad_table + (size_t)g.table_offset * C;
+#pragma unroll
+    for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+        float w = 1;
+        uint32_t p[D];
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+            if ((corner & (1u << d)) == 0) {
+                w *= 1 - cell.frac[d];
+                p[d] = cell.base[d];
+            } else {
+                w *= cell.frac[d];
+                p[d] = cell.base[d] + 1;
+            }
+        }
+        const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
+        T *dst = gt + (size_t)row * C;
+        if constexpr (C % 2 == 0) {
+#pragma unroll
+            for (uint32_t c = 0; c < C; c += 2) atomic_add_pair<T>(dst + c, w * gv[c], w * gv[c + 1]);
+        } else {
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) atomic_add_one(dst + c, w * gv[c]);
+        }
+    }
+}
+
+// gridencoder.cu:364-390: grad_inputs[b,d] = sum_{l,c} grad[l,b,c] * dy_dx[b,l,d,c]
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(kBwdThreads)
+k_grid_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__restrict__ grad_inputs,
+                 uint32_t B, uint32_t L, int layout) {
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= B * D) return;
+    const uint32_t b = t / D, d = t - b * D;
+    const T *dd = dy_dx + (size_t)b * L * D * C;
+    T acc = Num<T>::from_f(0.f);  // accumulated in T like the reference (`scalar_t result`)
+    for (uint32_t l = 0; l < L; ++l) {
+        const T *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)l * B + b) * C
+                                                 : grad + ((size_t)b * L + l) * C;
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c)
+            acc = Num<T>::from_f(Num<T>::to_f(acc) +
+                                 Num<T>::to_f(Num<T>::from_f(Num<T>::to_f(gp[c]) *
+                                                             Num<T>::to_f(dd[(l * D + d) * C + c]))));
+    }
+    grad_inputs[t] = acc;
+}
+
+template <typename T, uint32_t D, uint32_t C>
+int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *out, uint32_t B,
+            uint32_t L, float S, uint32_t H, void *dy_dx, uint32_t gridtype, bool ac, uint32_t interp,
+            int layout, cudaStream_t st) {
+    const uint32_t F = L * C;
+    const size_t smem = (layout == LNB_LAYOUT_BLC)
+                            ? (size_t)kTileB * (F + (sizeof(T) == 2 ? 2 : 1)) * sizeof(T) : 0;
+    if (smem > 200 * 1024) return LNB_ERR_UNSUPPORTED;
+    auto kern = k_grid_fwd<T, D, C>;
+    if (smem > 48 * 1024)
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const unsigned threads = (L >= 16) ? kFwdThreads : max(32u, min((unsigned)kFwdThreads, L * 32u));
+    kern<<<ceil_div<uint32_t>(B, kTileB), threads, smem, st>>>(
+        inputs, static_cast<const T *>(emb), offsets, static_cast<T *>(out), B, L, S, H,
+        static_cast<T *>(dy_dx), gridtype, ac, interp, layout);
+    count_launch();
+    return launch_status();
+}
+
+template <typename T, uint32_t D, uint32_t C>
+int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void *grad_emb, uint32_t B,
+            uint32_t L, float S, uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
+            bool ac, uint32_t interp, int layout, cudaStream_t st) {
+    dim3 grid(ceil_div<uint32_t>(B, kBwdThreads), L);
+    k_grid_bwd<T, D, C><<<grid, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
+                                                      static_cast<T *>(grad_emb), B, L, S, H,
+                                                      gridtype, ac, interp, layout);
+    count_launch();
+    int rc = launch_status();
+    if (rc != LNB_OK) return rc;
+    if (dy_dx) {
+        if (!grad_inputs) return LNB_ERR_INVALID_ARGUMENT;
+        k_grid_input_bwd<T, D, C><<<ceil_div<uint32_t>(B * D, kBwdThreads), kBwdThreads, 0, st>>>(
+            static_cast<const T *>(grad), static_cast<const T *>(dy_dx), static_cast<T *>(grad_inputs),
+            B, L, layout);
+        count_launch();
+        rc = launch_status();
+    }
+    return rc;
+}
+
+}  // namespace
+}  // namespace lnb
+
+using namespace lnb;
+
+#define LNB_GRID_DISPATCH(FN, ...)                                                             \
+    do {                                                                                       \
+        if (dtype == LNB_F32) {                                                                \
+            if (D == 3) {                                                                      \
+                switch (C) {                                                                   \
+                    case 1: return FN<float, 3, 1>(__VA_ARGS__);                               \
+                    case 2: return FN<float, 3, 2>(__VA_ARGS__);                               \
+                    case 4: return FN<float, 3, 4>(__VA_ARGS__);                               \
+                    case 8: return FN<float, 3, 8>(__VA_ARGS__);                               \
+                }                                                                              \
+            } else if (D == 2) {                                                               \
+                switch (C) {                                                                   \
+                    case 1: return FN<float, 2, 1>(__VA_ARGS__);                               \
+                    case 2: return FN<float, 2, 2>(__VA_ARGS__);                               \
+                    case 4: return FN<float, 2, 4>(__VA_ARGS__);                               \
+                    case 8: return FN<float, 2, 8>(__VA_ARGS__);                               \
+                }                                                                              \
+            }                                                                                  \
+        } else if (dtype == LNB_F16) {                                                         \
+            if (D == 3) {                                                                      \
+                switch (C) {                                                                   \
+                    case 1: return FN<__half, 3, 1>(__VA_ARGS__);                              \
+                    case 2: return FN<__half, 3, 2>(__VA_ARGS__);                              \
+                    case 4: return FN<__half, 3, 4>(__VA_ARGS__);                              \
+                    case 8: return FN<__half, 3, 8>(__VA_ARGS__);                              \
+                }                                                                              \
+            } else if (D == 2) {                                                               \
+                switch (C) {                                                                   \
+                    case 1: return FN<__half, 2, 1>(__VA_ARGS__);                              \
+                    case 2: return FN<__half, 2, 2>(__VA_ARGS__);                              \
+                    case 4: return FN<__half, 2, 4>(__VA_ARGS__);                              \
+                    case 8: return FN<__half, 2, 8>(__VA_ARGS__);                              \
+                }                                                                              \
+            }                                                                                  \
+        }                                                                                      \
+        return LNB_ERR_UNSUPPORTED;                                                            \
+    } while (0)
+
+extern "C" {
+
+int lnb_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets,
+                            void *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
+                            uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners,
+                            uint32_t interp, int dtype, int layout, lnb_stream_t stream) {
+    if (!inputs || !embeddings || !offsets || !outputs) return LNB_ERR_INVALID_ARGUMENT;
+    if (gridtype > 1 || interp > 1 || (layout != LNB_LAYOUT_LBC && layout != LNB_LAYOUT_BLC) || L == 0)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (B == 0) return LNB_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool ac = align_corners != 0;
+    LNB_GRID_DISPATCH(run_fwd, inputs, embeddings, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac,
+                      interp, layout, st);
+}
+
+int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings,
+                             const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D,
+                             uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx,
+                             void *grad_inputs, uint32_t gridtype, int align_corners,
+                             uint32_t interp, int dtype, int layout, lnb_stream_t stream) {
+    (void)embeddings;  // the table values are not needed for the table gradient (kept for ABI parity)
+    if (!grad || !inputs || !offsets || !grad_embeddings) return LNB_ERR_INVALID_ARGUMENT;
+    if (gridtype > 1 || interp > 1 || (layout != LNB_LAYOUT_LBC && layout != LNB_LAYOUT_BLC) || L == 0)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (B == 0) return LNB_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool ac = align_corners != 0;
+    LNB_GRID_DISPATCH(run_bwd, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs,
+                      gridtype, ac, interp, layout, st);
+}
+
+}  // extern "C"
