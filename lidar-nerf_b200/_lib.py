@@ -1,0 +1,49 @@
+"""ctypes loader for liblnb200.so, the C-ABI CUDA library declared in include/lidarnerf_b200.h.
+
+There is NO CPU fallback: if the library is missing the import fails loudly, and every entry point raises
+RuntimeError on a non-zero status (CUDA error or rejected argument), like TORCH_CHECK in the reference
+bindings (e.g. gridencoder.cu:608-624).
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "liblnb200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found. Build it with `python lidar-nerf_b200/build.py` (needs nvcc; sm_100a only). "
+        "lidar-nerf_b200 has no CPU fallback.")
+
+lib = C.CDLL(LIB_PATH)
+lib.lnb_strerror.restype = C.c_char_p
+lib.lnb_strerror.argtypes = [C.c_int]
+lib.lnb_arch.restype = C.c_char_p
+lib.lnb_launch_count.restype = C.c_uint64
+lib.lnb_ffmlp_backward_workspace_bytes.restype = C.c_size_t
+lib.lnb_ffmlp_backward_workspace_bytes.argtypes = [C.c_uint32] * 4
+
+u32, f32, i32, vp, sz = C.c_uint32, C.c_float, C.c_int, C.c_void_p, C.c_size_t
+
+# every exported symbol of include/lidarnerf_b200.h (tests check the .so exports all of them)
+SYMBOLS = [
+    "lnb_strerror", "lnb_version", "lnb_arch", "lnb_launch_count",
+    "lnb_near_far_from_aabb", "lnb_sph_from_ray", "lnb_morton3D", "lnb_morton3D_invert", "lnb_packbits",
+    "lnb_march_rays_train", "lnb_composite_rays_train_forward", "lnb_composite_rays_train_backward",
+    "lnb_composite_rays_train_forward_ex", "lnb_composite_rays_train_backward_ex",
+    "lnb_march_rays", "lnb_composite_rays",
+    "lnb_grid_encode_forward", "lnb_grid_encode_backward",
+    "lnb_freq_encode_forward", "lnb_freq_encode_backward",
+    "lnb_sh_encode_forward", "lnb_sh_encode_backward",
+    "lnb_ffmlp_forward", "lnb_ffmlp_inference", "lnb_ffmlp_backward_workspace_bytes", "lnb_ffmlp_backward",
+    "lnb_allocate_splitk", "lnb_free_splitk", "lnb_adam_step",
+]
+
+
+def check(status, what):
+    if status != 0:
+        raise RuntimeError(f"{what}: {lib.lnb_strerror(int(status)).decode()} (status {int(status)})")
+
+
+def launch_count():
+    return int(lib.lnb_launch_count())

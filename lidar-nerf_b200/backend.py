@@ -1,0 +1,300 @@
+"""Boundary B1: the five `_backend` modules of the reference, re-created over the C ABI.
+
+The reference's Python wrappers call pybind11 modules `_raymarching`, `_gridencoder`, `_freqencoder`,
+`_shencoder`, `_ffmlp` (bindings.cpp in each extension).  The objects below expose the SAME function names
+with the SAME positional arguments (torch tensors pre-allocated by the caller, sizes passed redundantly),
+forward them to liblnb200.so with raw device pointers, and launch on torch's CURRENT stream (the reference
+uses the legacy default stream).  `install_reference_backends()` registers them under the reference's module
+names so the reference's own wrappers (`import _raymarching as _backend`, raymarching.py:5-8) bind to these
+kernels without modification.
+"""
+import sys
+import types
+
+import torch
+
+from ._lib import lib, check, u32, f32, i32, vp, sz
+
+_F16, _F32 = 1, 0
+
+
+def _stream():
+    return vp(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t, name, dtype=None, allow_none=False):
+    if t is None:
+        if allow_none:
+            return vp(0)
+        raise RuntimeError(f"{name} must be a tensor")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous tensor")
+    if dtype is not None and t.dtype != dtype:
+        raise RuntimeError(f"{name} must be a {dtype} tensor, got {t.dtype}")
+    return vp(t.data_ptr())
+
+
+def _fp(t, name, allow_none=False):
+    return _ptr(t, name, torch.float32, allow_none)
+
+
+def _ip(t, name):
+    return _ptr(t, name, torch.int32)
+
+
+# ------------------------------------------------------------------------------------------ _raymarching
+class _Raymarching:
+    """raymarching/src/bindings.cpp:5-21"""
+
+    @staticmethod
+    def near_far_from_aabb(rays_o, rays_d, aabb, N, min_near, nears, fars):
+        check(lib.lnb_near_far_from_aabb(_fp(rays_o, "rays_o"), _fp(rays_d, "rays_d"), _fp(aabb, "aabb"), u32(N),
+                                         f32(min_near), _fp(nears, "nears"), _fp(fars, "fars"), _stream()),
+              "near_far_from_aabb")
+
+    @staticmethod
+    def sph_from_ray(rays_o, rays_d, radius, N, coords):
+        check(lib.lnb_sph_from_ray(_fp(rays_o, "rays_o"), _fp(rays_d, "rays_d"), f32(radius), u32(N),
+                                   _fp(coords, "coords"), _stream()), "sph_from_ray")
+
+    @staticmethod
+    def morton3D(coords, N, indices):
+        check(lib.lnb_morton3D(_ip(coords, "coords"), u32(N), _ip(indices, "indices"), _stream()), "morton3D")
+
+    @staticmethod
+    def morton3D_invert(indices, N, coords):
+        check(lib.lnb_morton3D_invert(_ip(indices, "indices"), u32(N), _ip(coords, "coords"), _stream()),
+              "morton3D_invert")
+
+    @staticmethod
+    def packbits(grid, N, density_thresh, bitfield):
+        check(lib.lnb_packbits(_fp(grid, "grid"), u32(N), f32(density_thresh),
+                               _ptr(bitfield, "bitfield", torch.uint8), _stream()), "packbits")
+
+    @staticmethod
+    def march_rays_train(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                         deltas, rays, counter, noises):
+        check(lib.lnb_march_rays_train(_fp(rays_o, "rays_o"), _fp(rays_d, "rays_d"), _ptr(grid, "grid", torch.uint8),
+                                       f32(bound), f32(dt_gamma), u32(max_steps), u32(N), u32(C), u32(H), u32(M),
+                                       _fp(nears, "nears"), _fp(fars, "fars"), _fp(xyzs, "xyzs"), _fp(dirs, "dirs"),
+                                       _fp(deltas, "deltas"), _ip(rays, "rays"), _ip(counter, "counter"),
+                                       _fp(noises, "noises"), _stream()), "march_rays_train")
+
+    @staticmethod
+    def composite_rays_train_forward(sigmas, rgbs, deltas, rays, M, N, T_thresh, weights_sum, depth, image):
+        check(lib.lnb_composite_rays_train_forward(_fp(sigmas, "sigmas"), _fp(rgbs, "rgbs"), _fp(deltas, "deltas"),
+                                                   _ip(rays, "rays"), u32(M), u32(N), f32(T_thresh),
+                                                   _fp(weights_sum, "weights_sum"), _fp(depth, "depth"),
+                                                   _fp(image, "image"), _stream()), "composite_rays_train_forward")
+
+    @staticmethod
+    def composite_rays_train_backward(grad_weights_sum, grad_image, sigmas, rgbs, deltas, rays, weights_sum, image,
+                                      M, N, T_thresh, grad_sigmas, grad_rgbs):
+        check(lib.lnb_composite_rays_train_backward(
+            _fp(grad_weights_sum, "grad_weights_sum"), _fp(grad_image, "grad_image"), _fp(sigmas, "sigmas"),
+            _fp(rgbs, "rgbs"), _fp(deltas, "deltas"), _ip(rays, "rays"), _fp(weights_sum, "weights_sum"),
+            _fp(image, "image"), u32(M), u32(N), f32(T_thresh), _fp(grad_sigmas, "grad_sigmas"),
+            _fp(grad_rgbs, "grad_rgbs"), _stream()), "composite_rays_train_backward")
+
+    # extensions (not in the reference): arbitrary channel count and the depth gradient
+    @staticmethod
+    def composite_rays_train_forward_ex(sigmas, rgbs, deltas, rays, M, N, T_thresh, channels, weights_sum, depth,
+                                        image):
+        check(lib.lnb_composite_rays_train_forward_ex(_fp(sigmas, "sigmas"), _fp(rgbs, "rgbs"), _fp(deltas, "deltas"),
+                                                      _ip(rays, "rays"), u32(M), u32(N), f32(T_thresh), u32(channels),
+                                                      _fp(weights_sum, "weights_sum"), _fp(depth, "depth"),
+                                                      _fp(image, "image"), _stream()),
+              "composite_rays_train_forward_ex")
+
+    @staticmethod
+    def composite_rays_train_backward_ex(grad_weights_sum, grad_depth, grad_image, sigmas, rgbs, deltas, rays,
+                                         weights_sum, depth, image, M, N, T_thresh, channels, grad_sigmas, grad_rgbs):
+        check(lib.lnb_composite_rays_train_backward_ex(
+            _fp(grad_weights_sum, "grad_weights_sum"), _fp(grad_depth, "grad_depth", True),
+            _fp(grad_image, "grad_image"), _fp(sigmas, "sigmas"), _fp(rgbs, "rgbs"), _fp(deltas, "deltas"),
+            _ip(rays, "rays"), _fp(weights_sum, "weights_sum"), _fp(depth, "depth", True), _fp(image, "image"),
+            u32(M), u32(N), f32(T_thresh), u32(channels), _fp(grad_sigmas, "grad_sigmas"),
+            _fp(grad_rgbs, "grad_rgbs"), _stream()), "composite_rays_train_backward_ex")
+
+    @staticmethod
+    def march_rays(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid,
+                   nears, fars, xyzs, dirs, deltas, noises):
+        check(lib.lnb_march_rays(u32(n_alive), u32(n_step), _ip(rays_alive, "rays_alive"), _fp(rays_t, "rays_t"),
+                                 _fp(rays_o, "rays_o"), _fp(rays_d, "rays_d"), f32(bound), f32(dt_gamma),
+                                 u32(max_steps), u32(C), u32(H), _ptr(grid, "grid", torch.uint8), _fp(nears, "nears"),
+                                 _fp(fars, "fars"), _fp(xyzs, "xyzs"), _fp(dirs, "dirs"), _fp(deltas, "deltas"),
+                                 _fp(noises, "noises"), _stream()), "march_rays")
+
+    @staticmethod
+    def composite_rays(n_alive, n_step, T_thresh, rays_alive, rays_t, sigmas, rgbs, deltas, weights_sum, depth,
+                       image):
+        check(lib.lnb_composite_rays(u32(n_alive), u32(n_step), f32(T_thresh), _ip(rays_alive, "rays_alive"),
+                                     _fp(rays_t, "rays_t"), _fp(sigmas, "sigmas"), _fp(rgbs, "rgbs"),
+                                     _fp(deltas, "deltas"), _fp(weights_sum, "weights_sum"), _fp(depth, "depth"),
+                                     _fp(image, "image"), _stream()), "composite_rays")
+
+
+# ------------------------------------------------------------------------------------------ _gridencoder
+def _grid_dtype(t, name):
+    if t.dtype == torch.float32:
+        return _F32
+    if t.dtype == torch.float16:
+        return _F16
+    raise RuntimeError(f"{name} must be a float32 or float16 tensor (got {t.dtype})")
+
+
+class _GridEncoder:
+    """gridencoder/src/bindings.cpp:5-11.  `layout` (keyword, default 0 = the reference's [L,B,C]) is an
+    extension: 1 = [B, L*C]."""
+
+    @staticmethod
+    def grid_encode_forward(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype, align_corners,
+                            interp, layout=0):
+        dt = _grid_dtype(embeddings, "embeddings")
+        check(lib.lnb_grid_encode_forward(_fp(inputs, "inputs"), _ptr(embeddings, "embeddings"), _ip(offsets, "offsets"),
+                                          _ptr(outputs, "outputs", embeddings.dtype), u32(B), u32(D), u32(C), u32(L),
+                                          f32(S), u32(H),
+                                          _ptr(dy_dx, "dy_dx", embeddings.dtype, allow_none=True), u32(gridtype),
+                                          i32(int(bool(align_corners))), u32(interp), i32(dt), i32(layout), _stream()),
+              "grid_encode_forward")
+
+    @staticmethod
+    def grid_encode_backward(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H, dy_dx, grad_inputs,
+                             gridtype, align_corners, interp, layout=0):
+        dt = _grid_dtype(grad, "grad")
+        check(lib.lnb_grid_encode_backward(_ptr(grad, "grad"), _fp(inputs, "inputs"), _ptr(embeddings, "embeddings"),
+                                           _ip(offsets, "offsets"),
+                                           _ptr(grad_embeddings, "grad_embeddings", grad.dtype), u32(B), u32(D), u32(C),
+                                           u32(L), f32(S), u32(H), _ptr(dy_dx, "dy_dx", grad.dtype, allow_none=True),
+                                           _ptr(grad_inputs, "grad_inputs", grad.dtype, allow_none=True),
+                                           u32(gridtype), i32(int(bool(align_corners))), u32(interp), i32(dt),
+                                           i32(layout), _stream()), "grid_encode_backward")
+
+    @staticmethod
+    def grad_total_variation(*args, **kwargs):
+        # gridencoder.cu:695-911 has no caller in the reference - out of scope.
+        raise NotImplementedError("grad_total_variation is outside the hot path this library implements")
+
+
+# ------------------------------------------------------------------------------------------ _freqencoder
+class _FreqEncoder:
+    """freqencoder/src/bindings.cpp:5-9"""
+
+    @staticmethod
+    def freq_encode_forward(inputs, B, D, deg, C, outputs):
+        check(lib.lnb_freq_encode_forward(_fp(inputs, "inputs"), u32(B), u32(D), u32(deg), u32(C),
+                                          _fp(outputs, "outputs"), _stream()), "freq_encode_forward")
+
+    @staticmethod
+    def freq_encode_backward(grad, outputs, B, D, deg, C, grad_inputs):
+        check(lib.lnb_freq_encode_backward(_fp(grad, "grad"), _fp(outputs, "outputs"), u32(B), u32(D), u32(deg),
+                                           u32(C), _fp(grad_inputs, "grad_inputs"), _stream()), "freq_encode_backward")
+
+
+# ------------------------------------------------------------------------------------------ _shencoder
+class _SHEncoder:
+    """shencoder/src/bindings.cpp:5-8"""
+
+    @staticmethod
+    def sh_encode_forward(inputs, outputs, B, D, C, dy_dx):
+        check(lib.lnb_sh_encode_forward(_fp(inputs, "inputs"), _fp(outputs, "outputs"), u32(B), u32(D), u32(C),
+                                        _fp(dy_dx, "dy_dx", True), _stream()), "sh_encode_forward")
+
+    @staticmethod
+    def sh_encode_backward(grad, inputs, B, D, C, dy_dx, grad_inputs):
+        check(lib.lnb_sh_encode_backward(_fp(grad, "grad"), _fp(inputs, "inputs"), u32(B), u32(D), u32(C),
+                                         _fp(dy_dx, "dy_dx"), _fp(grad_inputs, "grad_inputs"), _stream()),
+              "sh_encode_backward")
+
+
+# ------------------------------------------------------------------------------------------ _ffmlp
+_ffmlp_ws = {}
+
+
+def _hp(t, name, allow_none=False):
+    return _ptr(t, name, torch.float16, allow_none)
+
+
+def ffmlp_workspace(device, input_dim, output_dim, hidden_dim, num_layers):
+    """fp32 scratch for the weight-gradient accumulators (cached per device/shape/stream)."""
+    need = int(lib.lnb_ffmlp_backward_workspace_bytes(input_dim, output_dim, hidden_dim, num_layers))
+    key = (device, input_dim, output_dim, hidden_dim, num_layers, torch.cuda.current_stream().cuda_stream)
+    ws = _ffmlp_ws.get(key)
+    if ws is None:
+        ws = torch.empty(need // 4, dtype=torch.float32, device=device)
+        _ffmlp_ws[key] = ws
+    return ws, need
+
+
+class _FFMLP:
+    """ffmlp/src/bindings.cpp:5-10"""
+
+    @staticmethod
+    def ffmlp_forward(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation,
+                      output_activation, forward_buffer, outputs):
+        check(lib.lnb_ffmlp_forward(_hp(inputs, "inputs"), _hp(weights, "weights"), u32(B), u32(input_dim),
+                                    u32(output_dim), u32(hidden_dim), u32(num_layers), u32(activation),
+                                    u32(output_activation), _hp(forward_buffer, "forward_buffer"),
+                                    _hp(outputs, "outputs"), _stream()), "ffmlp_forward")
+
+    @staticmethod
+    def ffmlp_inference(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation,
+                        output_activation, inference_buffer, outputs):
+        check(lib.lnb_ffmlp_inference(_hp(inputs, "inputs"), _hp(weights, "weights"), u32(B), u32(input_dim),
+                                      u32(output_dim), u32(hidden_dim), u32(num_layers), u32(activation),
+                                      u32(output_activation), _hp(inference_buffer, "inference_buffer", True),
+                                      _hp(outputs, "outputs"), _stream()), "ffmlp_inference")
+
+    @staticmethod
+    def ffmlp_backward(grad, inputs, weights, forward_buffer, B, input_dim, output_dim, hidden_dim, num_layers,
+                       activation, output_activation, calc_grad_inputs, backward_buffer, grad_inputs, grad_weights):
+        ws, need = ffmlp_workspace(grad.device, input_dim, output_dim, hidden_dim, num_layers)
+        check(lib.lnb_ffmlp_backward(_hp(grad, "grad"), _hp(inputs, "inputs"), _hp(weights, "weights"),
+                                     _hp(forward_buffer, "forward_buffer"), u32(B), u32(input_dim), u32(output_dim),
+                                     u32(hidden_dim), u32(num_layers), u32(activation), u32(output_activation),
+                                     i32(int(bool(calc_grad_inputs))), _hp(backward_buffer, "backward_buffer", True),
+                                     _hp(grad_inputs, "grad_inputs") if calc_grad_inputs else vp(0),
+                                     _hp(grad_weights, "grad_weights", True), vp(ws.data_ptr()), sz(need),
+                                     _stream()), "ffmlp_backward")
+        return ws
+
+    @staticmethod
+    def allocate_splitk(size):
+        check(lib.lnb_allocate_splitk(sz(size)), "allocate_splitk")
+
+    @staticmethod
+    def free_splitk():
+        check(lib.lnb_free_splitk(), "free_splitk")
+
+
+# ------------------------------------------------------------------------------------------ optimiser
+def adam_step(params, grad, exp_avg, exp_avg_sq, params_half, lr, beta1, beta2, eps, step, grad_scale=1.0,
+              zero_grad=True):
+    bc1, bc2 = 1.0 - beta1 ** step, 1.0 - beta2 ** step
+    check(lib.lnb_adam_step(_fp(params, "params"), _fp(grad, "grad"), _fp(exp_avg, "exp_avg"),
+                            _fp(exp_avg_sq, "exp_avg_sq"), _hp(params_half, "params_half", True), sz(params.numel()),
+                            f32(lr), f32(beta1), f32(beta2), f32(eps), f32(bc1), f32(bc2), f32(grad_scale),
+                            i32(int(zero_grad)), _stream()), "adam_step")
+
+
+_raymarching = _Raymarching()
+_gridencoder = _GridEncoder()
+_freqencoder = _FreqEncoder()
+_shencoder = _SHEncoder()
+_ffmlp = _FFMLP()
+
+_BACKENDS = {"_raymarching": _raymarching, "_gridencoder": _gridencoder, "_grid_encoder": _gridencoder,
+             "_freqencoder": _freqencoder, "_shencoder": _shencoder, "_sh_encoder": _shencoder, "_ffmlp": _ffmlp}
+
+
+def install_reference_backends():
+    """Register the B1 objects as importable modules under the names the reference's wrappers import
+    (`import _raymarching as _backend`, etc.), so those wrappers run unmodified on these kernels."""
+    for name, obj in _BACKENDS.items():
+        mod = types.ModuleType(name)
+        for attr in dir(obj):
+            if not attr.startswith("__"):
+                setattr(mod, attr, getattr(obj, attr))
+        sys.modules[name] = mod

@@ -1,0 +1,82 @@
+"""CPU-only checks of the drop-in boundary: the C-ABI library loads, exports every symbol include/*.h declares,
+and rejects bad arguments before touching the GPU (no compute calls here)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def L():
+    from lidar_nerf_b200 import _lib
+    return _lib
+
+
+def header_symbols():
+    text = open(os.path.join(ROOT, "include", "lidarnerf_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(lnb_[A-Za-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(L):
+    syms = header_symbols()
+    assert len(syms) >= 28
+    for s in syms:
+        assert hasattr(L.lib, s), f"liblnb200.so does not export {s}"
+    assert sorted(L.SYMBOLS) == syms, "lidar-nerf_b200/_lib.py SYMBOLS out of sync with the header"
+
+
+def test_arch_and_status_strings(L):
+    assert L.lib.lnb_arch() == b"sm_100a"
+    assert L.lib.lnb_strerror(0) == b"ok"
+    for code in (-1, -2, -3, -4):
+        assert b"lidarnerf_b200" in L.lib.lnb_strerror(code)
+
+
+def test_null_pointers_are_rejected_without_a_gpu(L):
+    z = C.c_void_p(0)
+    u = C.c_uint32
+    assert L.lib.lnb_near_far_from_aabb(z, z, z, u(4), C.c_float(0.1), z, z, z) == -1
+    assert L.lib.lnb_march_rays_train(z, z, z, C.c_float(1), C.c_float(0), u(8), u(4), u(1), u(128), u(32), z, z, z, z,
+                                      z, z, z, z, z) == -1
+    assert L.lib.lnb_grid_encode_forward(z, z, z, z, u(4), u(3), u(2), u(16), C.c_float(1), u(16), z, u(0), C.c_int(0),
+                                         u(0), C.c_int(0), C.c_int(0), z) == -1
+    assert L.lib.lnb_ffmlp_forward(z, z, u(128), u(32), u(16), u(64), u(2), u(0), u(6), z, z, z) == -1
+    with pytest.raises(RuntimeError, match="invalid argument"):
+        L.check(-1, "probe")
+
+
+def test_ffmlp_workspace_size(L):
+    assert L.lib.lnb_ffmlp_backward_workspace_bytes(32, 16, 64, 2) == 4 * 64 * (32 + 64 + 16)
+
+
+def test_b1_backends_have_the_reference_function_names():
+    from lidar_nerf_b200 import backend as be
+    ref = {
+        "_raymarching": ["packbits", "near_far_from_aabb", "sph_from_ray", "morton3D", "morton3D_invert",
+                         "march_rays_train", "composite_rays_train_forward", "composite_rays_train_backward",
+                         "march_rays", "composite_rays"],
+        "_gridencoder": ["grid_encode_forward", "grid_encode_backward", "grad_total_variation"],
+        "_freqencoder": ["freq_encode_forward", "freq_encode_backward"],
+        "_shencoder": ["sh_encode_forward", "sh_encode_backward"],
+        "_ffmlp": ["ffmlp_forward", "ffmlp_inference", "ffmlp_backward", "allocate_splitk", "free_splitk"],
+    }
+    for mod, names in ref.items():
+        obj = getattr(be, mod)
+        for n in names:
+            assert callable(getattr(obj, n)), f"{mod}.{n} missing"
+    import sys
+    be.install_reference_backends()
+    import _raymarching, _gridencoder, _freqencoder, _shencoder, _ffmlp  # noqa: F401,E401
+    assert callable(sys.modules["_raymarching"].march_rays_train)
+
+
+def test_cpu_tensors_are_rejected_like_torch_check():
+    import torch
+    from lidar_nerf_b200 import backend as be
+    x = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        be._freqencoder.freq_encode_forward(x, 4, 3, 2, 15, torch.zeros(4, 15))

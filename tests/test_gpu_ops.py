@@ -1,0 +1,477 @@
+"""GPU parity tests (run with `-m gpu` on the B200 box): every C-ABI entry point of liblnb200.so, called through
+the B1 backend objects, against the CPU oracle on the same seeded inputs - and against the UNMODIFIED reference
+CUDA kernels (oracle/_ref, when present) for the bit-exactness claims.
+
+Tolerances (written here, per the north-star):
+  * march sample counts / offsets / cell decisions: bit-exact; positions and deltas: bit-exact vs the reference
+    CUDA kernel, <= 1 ulp-level (1e-6 abs) vs the CPU oracle (libm vs device frexp/scalbn are exact; FMA placement
+    is mirrored);
+  * fp32 outputs (composite, encoders): rtol 1e-4, atol 1e-5 (fast-math __expf/__sinf vs libm);
+  * fp16 MLP: within 2 fp16 ulps of the fp32-accumulating oracle (rtol 2e-3, atol 2e-3) - the reference itself
+    accumulates in fp16 and is no closer.
+"""
+import numpy as np
+import pytest
+import torch
+
+import cases
+import refcuda
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def T(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).to(DEV)
+    return t if dtype is None else t.to(dtype)
+
+
+def N_(t):
+    return t.detach().float().cpu().numpy() if t.dtype in (torch.float16, torch.float32) else t.detach().cpu().numpy()
+
+
+@pytest.fixture(scope="module")
+def be():
+    from lidar_nerf_b200 import backend
+    return backend
+
+
+def by_ray(rays, xyzs, deltas):
+    """-> counts[N] in ray order and samples re-packed in ray order."""
+    rays = N_(rays)
+    order = np.argsort(rays[:, 0], kind="stable")
+    rays = rays[order]
+    assert (rays[:, 0] == np.arange(len(rays))).all(), "every ray id must appear exactly once"
+    xs, ds = N_(xyzs), N_(deltas)
+    px = [xs[o:o + n] for _, o, n in rays]
+    pd = [ds[o:o + n] for _, o, n in rays]
+    return rays[:, 2], (np.concatenate(px) if px else xs[:0]), (np.concatenate(pd) if pd else ds[:0])
+
+
+def run_march(backend, c, nears, fars, dt_gamma, max_steps, M=None):
+    N = c["rays_o"].shape[0]
+    M = N * max_steps if M is None else M
+    xyzs, dirs, deltas = torch.zeros(M, 3, device=DEV), torch.zeros(M, 3, device=DEV), torch.zeros(M, 2, device=DEV)
+    rays = torch.full((N, 3), -1, dtype=torch.int32, device=DEV)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    backend.march_rays_train(T(c["rays_o"]), T(c["rays_d"]), T(c["bitfield"]), c["bound"], dt_gamma, max_steps, N,
+                             c["cascade"], c["H"], M, T(nears), T(fars), xyzs, dirs, deltas, rays, counter,
+                             T(c["noises"]))
+    torch.cuda.synchronize()
+    return xyzs, dirs, deltas, rays, counter
+
+
+MARCH = [
+    dict(seed=11, N=256, cascade=1, bound=1.0, fill=0.3, lidar=False, dt_gamma=0.0, max_steps=1024),
+    dict(seed=12, N=256, cascade=1, bound=1.0, fill=0.15, lidar=True, dt_gamma=0.0, max_steps=1024),
+    dict(seed=13, N=256, cascade=3, bound=4.0, fill=0.3, lidar=False, dt_gamma=1.0 / 128, max_steps=128),
+    dict(seed=14, N=128, cascade=1, bound=1.0, fill=0.9, lidar=False, dt_gamma=1.0 / 128, max_steps=64),
+    dict(seed=17, N=33, cascade=2, bound=2.0, fill=0.0, lidar=False, dt_gamma=0.0, max_steps=256),   # empty grid
+    dict(seed=18, N=65, cascade=1, bound=1.0, fill=1.0, lidar=False, dt_gamma=0.0, max_steps=300),   # full grid
+]
+
+
+def near_far(orc, c, lidar):
+    N = c["rays_o"].shape[0]
+    if lidar:
+        nears = np.full(N, 0.0108, np.float32)
+        return nears, nears * np.float32(81.0)
+    b = c["bound"]
+    return orc.near_far_from_aabb(c["rays_o"], c["rays_d"], np.array([-b, -b, -b, b, b, b], np.float32), 0.05)
+
+
+@pytest.mark.parametrize("cs", MARCH, ids=lambda c: f"seed{c['seed']}")
+def test_march_rays_train_vs_oracle_and_reference(be, orc, cs):
+    c = cases.march_case(cs["seed"], cs["N"], cs["cascade"], cs["bound"], 128, cs["fill"], cs["lidar"])
+    nears, fars = near_far(orc, c, cs["lidar"])
+    xyzs, dirs, deltas, rays, counter = run_march(be._raymarching, c, nears, fars, cs["dt_gamma"], cs["max_steps"])
+    counts, px, pd = by_ray(rays, xyzs, deltas)
+    assert int(counter[0]) == counts.sum() and int(counter[1]) == cs["N"]
+
+    o_x, o_d, o_dl, o_rays, o_counter = orc.march_rays_train(c["rays_o"], c["rays_d"], c["bound"], c["bitfield"],
+                                                              c["cascade"], c["H"], nears, fars, c["noises"],
+                                                              cs["dt_gamma"], cs["max_steps"])
+    np.testing.assert_array_equal(counts, o_rays[:, 2], err_msg="sample counts differ from the CPU oracle")
+    tot = int(o_counter[0])
+    np.testing.assert_allclose(px, o_x[:tot], rtol=0, atol=1e-6)
+    np.testing.assert_allclose(pd, o_dl[:tot], rtol=0, atol=1e-6)
+    # dirs are copies of the ray direction
+    rr = N_(rays)
+    for rid, off, n in rr[:8]:
+        if n:
+            np.testing.assert_array_equal(N_(dirs)[off:off + n], np.tile(c["rays_d"][rid], (n, 1)))
+
+    ref = refcuda.load("_raymarching")
+    if ref is not None:
+        r_x, _, r_dl, r_rays, r_counter = run_march(ref, c, nears, fars, cs["dt_gamma"], cs["max_steps"])
+        r_counts, r_px, r_pd = by_ray(r_rays, r_x, r_dl)
+        np.testing.assert_array_equal(counts, r_counts, err_msg="sample counts differ from the reference CUDA kernel")
+        np.testing.assert_array_equal(px, r_px, err_msg="sample positions not bit-identical to the reference kernel")
+        np.testing.assert_array_equal(pd, r_pd, err_msg="deltas not bit-identical to the reference kernel")
+
+
+def test_march_overflow_drops_rays_like_reference(be, orc):
+    """M smaller than the produced count: rays whose span does not fit write nothing (raymarching.cu:456-457)."""
+    c = cases.march_case(19, 200, 1, 1.0, 128, 0.5, False)
+    nears, fars = near_far(orc, c, False)
+    full = run_march(be._raymarching, c, nears, fars, 0.0, 512)
+    total = int(full[4][0])
+    M = max(total // 2, 1)
+    xyzs, dirs, deltas, rays, counter = run_march(be._raymarching, c, nears, fars, 0.0, 512, M=M)
+    assert int(counter[0]) == total
+    rr = N_(rays)
+    dl = N_(deltas)
+    fits = rr[:, 1] + rr[:, 2] <= M
+    for rid, off, n in rr[fits][:20]:
+        assert (dl[off:off + n, 0] > 0).all()
+    # everything not covered by a fitting ray is still zero
+    mask = np.zeros(M, bool)
+    for rid, off, n in rr[fits]:
+        mask[off:off + n] = True
+    assert (dl[~mask] == 0).all()
+
+
+def test_small_raymarching_utils(be, orc):
+    rng = np.random.default_rng(1)
+    o = rng.uniform(-1.5, 1.5, size=(400, 3)).astype(np.float32)
+    d = cases.unit(rng.normal(size=(400, 3))).astype(np.float32)
+    d[:3] = np.eye(3)  # zero components
+    aabb = np.array([-1, -1, -1, 1, 1, 1], np.float32)
+    nears, fars = torch.empty(400, device=DEV), torch.empty(400, device=DEV)
+    be._raymarching.near_far_from_aabb(T(o), T(d), T(aabb), 400, 0.05, nears, fars)
+    on, of = orc.near_far_from_aabb(o, d, aabb, 0.05)
+    np.testing.assert_array_equal(N_(nears), on)
+    np.testing.assert_array_equal(N_(fars), of)
+
+    coords = torch.empty(400, 2, device=DEV)
+    be._raymarching.sph_from_ray(T(o * 0.3), T(d), 2.0, 400, coords)
+    np.testing.assert_allclose(N_(coords), orc.sph_from_ray(o * 0.3, d, 2.0), rtol=1e-5, atol=1e-5)
+
+    c3 = rng.integers(0, 1024, size=(500, 3)).astype(np.int32)
+    idx = torch.empty(500, dtype=torch.int32, device=DEV)
+    be._raymarching.morton3D(T(c3), 500, idx)
+    np.testing.assert_array_equal(N_(idx), orc.morton3D(c3))
+    back = torch.empty(500, 3, dtype=torch.int32, device=DEV)
+    be._raymarching.morton3D_invert(idx, 500, back)
+    np.testing.assert_array_equal(N_(back), c3)
+
+    grid = rng.uniform(0, 1, size=4096 * 8).astype(np.float32)
+    grid[:16] = 0.5  # equal to the threshold -> bit clear (strict >)
+    bits = torch.empty(4096, dtype=torch.uint8, device=DEV)
+    be._raymarching.packbits(T(grid), 4096, 0.5, bits)
+    np.testing.assert_array_equal(N_(bits), orc.packbits(grid, 0.5))
+
+    ref = refcuda.load("_raymarching")
+    if ref is not None:
+        n2, f2 = torch.empty(400, device=DEV), torch.empty(400, device=DEV)
+        ref.near_far_from_aabb(T(o), T(d), T(aabb), 400, 0.05, n2, f2)
+        assert torch.equal(n2, nears) and torch.equal(f2, fars)
+        c2 = torch.empty(400, 2, device=DEV)
+        ref.sph_from_ray(T(o * 0.3), T(d), 2.0, 400, c2)
+        np.testing.assert_allclose(N_(coords), N_(c2), rtol=1e-6, atol=1e-6)
+        b2 = torch.empty(4096, dtype=torch.uint8, device=DEV)
+        ref.packbits(T(grid).view(1, -1), 4096, 0.5, b2)
+        assert torch.equal(b2, bits)
+
+
+COMPOSITE = [dict(seed=21, N=300, max_count=200), dict(seed=22, N=64, max_count=700, opaque_frac=0.8),
+             dict(seed=23, N=5, max_count=3)]
+
+
+@pytest.mark.parametrize("cs", COMPOSITE, ids=lambda c: f"seed{c['seed']}")
+@pytest.mark.parametrize("ch", [3, 2])
+def test_composite_rays_train(be, orc, cs, ch):
+    c = cases.composite_case(ch=ch, **cs)
+    N, M = c["N"], c["M"]
+    sig, rgb, dl, rays = T(c["sigmas"]), T(c["rgbs"]), T(c["deltas"]), T(c["rays"])
+    ws, dep, img = torch.empty(N, device=DEV), torch.empty(N, device=DEV), torch.empty(N, ch, device=DEV)
+    rb = be._raymarching
+    if ch == 3:
+        rb.composite_rays_train_forward(sig, rgb, dl, rays, M, N, 1e-4, ws, dep, img)
+    else:
+        rb.composite_rays_train_forward_ex(sig, rgb, dl, rays, M, N, 1e-4, ch, ws, dep, img)
+    ows, odep, oimg = orc.composite_rays_train_forward(c["sigmas"], c["rgbs"], c["deltas"], c["rays"], 1e-4)
+    np.testing.assert_allclose(N_(ws), ows, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N_(dep), odep, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N_(img), oimg, rtol=1e-4, atol=1e-5)
+
+    rng = np.random.default_rng(cs["seed"] + 100)
+    gws, gimg = rng.normal(size=N).astype(np.float32), rng.normal(size=(N, ch)).astype(np.float32)
+    gdep = rng.normal(size=N).astype(np.float32)
+    for depth_grad in (False, True):
+        gs, gc = torch.zeros(M, device=DEV), torch.zeros(M, ch, device=DEV)
+        if ch == 3 and not depth_grad:
+            rb.composite_rays_train_backward(T(gws), T(gimg), sig, rgb, dl, rays, ws, img, M, N, 1e-4, gs, gc)
+        else:
+            rb.composite_rays_train_backward_ex(T(gws), T(gdep) if depth_grad else None, T(gimg), sig, rgb, dl, rays, ws,
+                                                dep if depth_grad else None, img, M, N, 1e-4, ch, gs, gc)
+        # the oracle is evaluated on OUR forward outputs, like the kernel
+        ogs, ogc = orc.composite_rays_train_backward(gws, gimg, c["sigmas"], c["rgbs"], c["deltas"], c["rays"], N_(ws),
+                                                     N_(img), 1e-4, gdep if depth_grad else None,
+                                                     N_(dep) if depth_grad else None)
+        scale = max(1.0, float(np.abs(ogs).max()))
+        np.testing.assert_allclose(N_(gs), ogs, rtol=2e-4, atol=2e-5 * scale)
+        np.testing.assert_allclose(N_(gc), ogc, rtol=1e-4, atol=1e-5)
+
+    ref = refcuda.load("_raymarching")
+    if ref is not None and ch == 3:
+        w2, d2, i2 = torch.empty(N, device=DEV), torch.empty(N, device=DEV), torch.empty(N, 3, device=DEV)
+        ref.composite_rays_train_forward(sig, rgb, dl, rays, M, N, 1e-4, w2, d2, i2)
+        np.testing.assert_allclose(N_(ws), N_(w2), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(N_(dep), N_(d2), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(N_(img), N_(i2), rtol=1e-4, atol=1e-6)
+        gs, gc = torch.zeros(M, device=DEV), torch.zeros(M, 3, device=DEV)
+        rb.composite_rays_train_backward(T(gws), T(gimg), sig, rgb, dl, rays, w2, i2, M, N, 1e-4, gs, gc)
+        gs2, gc2 = torch.zeros(M, device=DEV), torch.zeros(M, 3, device=DEV)
+        ref.composite_rays_train_backward(T(gws), T(gimg), sig, rgb, dl, rays, w2, i2, M, N, 1e-4, gs2, gc2)
+        scale = max(1.0, float(gs2.abs().max()))
+        np.testing.assert_allclose(N_(gs), N_(gs2), rtol=2e-4, atol=2e-5 * scale)
+        np.testing.assert_allclose(N_(gc), N_(gc2), rtol=1e-4, atol=1e-6)
+
+
+def test_composite_depth_gradient_matches_autograd(be):
+    """The depth-gradient extension against torch autograd on the same compositing formula."""
+    c = cases.composite_case(24, N=40, max_count=60, ch=2, opaque_frac=0.0)
+    N, M = c["N"], c["M"]
+    sig = T(c["sigmas"]).double().requires_grad_(True)
+    rgb = T(c["rgbs"]).double().requires_grad_(True)
+    dl = T(c["deltas"]).double()
+    tot_d, tot_w, tot_i = [], [], []
+    for rid, off, n in c["rays"]:
+        s, col, d0, d1 = sig[off:off + n], rgb[off:off + n], dl[off:off + n, 0], dl[off:off + n, 1]
+        alpha = 1 - torch.exp(-s * d0)
+        Tm = torch.cumprod(torch.cat([torch.ones(1, device=DEV, dtype=torch.double), 1 - alpha]), 0)[:-1]
+        w = alpha * Tm
+        t = torch.cumsum(d1, 0)
+        tot_d.append((w * t).sum()), tot_w.append(w.sum()), tot_i.append((w[:, None] * col).sum(0))
+    order = np.argsort(c["rays"][:, 0])
+    dep_t = torch.stack(tot_d)[torch.from_numpy(order).to(DEV)]
+    rng = np.random.default_rng(5)
+    gdep = rng.normal(size=N).astype(np.float32)
+    (dep_t * T(gdep).double()).sum().backward()
+
+    ws, dep, img = torch.empty(N, device=DEV), torch.empty(N, device=DEV), torch.empty(N, 2, device=DEV)
+    rb = be._raymarching
+    sig32, rgb32, dl32, rays = T(c["sigmas"]), T(c["rgbs"]), T(c["deltas"]), T(c["rays"])
+    rb.composite_rays_train_forward_ex(sig32, rgb32, dl32, rays, M, N, 0.0, 2, ws, dep, img)
+    np.testing.assert_allclose(N_(dep), dep_t.detach().cpu().numpy(), rtol=1e-4, atol=1e-6)
+    gs, gc = torch.zeros(M, device=DEV), torch.zeros(M, 2, device=DEV)
+    zero_n, zero_i = torch.zeros(N, device=DEV), torch.zeros(N, 2, device=DEV)
+    rb.composite_rays_train_backward_ex(zero_n, T(gdep), zero_i, sig32, rgb32, dl32, rays, ws, dep, img, M, N, 0.0, 2, gs,
+                                        gc)
+    np.testing.assert_allclose(N_(gs), sig.grad.cpu().numpy(), rtol=2e-3, atol=2e-5)
+
+
+def test_inference_march_and_composite(be, orc):
+    c = cases.march_case(15, 128, 1, 1.0, 128, 0.3, False)
+    N, n_step = 128, 8
+    nears, fars = near_far(orc, c, False)
+    alive = torch.arange(N, dtype=torch.int32, device=DEV)
+    rays_t = T(nears).clone()
+    xyzs, dirs, deltas = (torch.zeros(N * n_step, 3, device=DEV), torch.zeros(N * n_step, 3, device=DEV),
+                          torch.zeros(N * n_step, 2, device=DEV))
+    rb = be._raymarching
+    rb.march_rays(N, n_step, alive, rays_t, T(c["rays_o"]), T(c["rays_d"]), 1.0, 0.0, 1024, 1, 128, T(c["bitfield"]),
+                  T(nears), T(fars), xyzs, dirs, deltas, T(c["noises"]))
+    ox, od, odl = orc.march_rays(N, n_step, np.arange(N, dtype=np.int32), nears, c["rays_o"], c["rays_d"], 1.0,
+                                 c["bitfield"], 1, 128, nears, fars, c["noises"], 0.0, 1024)
+    np.testing.assert_allclose(N_(xyzs), ox, rtol=0, atol=1e-6)
+    np.testing.assert_allclose(N_(deltas), odl, rtol=0, atol=1e-6)
+
+    rng = np.random.default_rng(16)
+    sig = rng.gamma(1.0, 20.0, size=N * n_step).astype(np.float32)
+    rgb = rng.uniform(0, 1, size=(N * n_step, 3)).astype(np.float32)
+    ws, dep, img = torch.zeros(N, device=DEV), torch.zeros(N, device=DEV), torch.zeros(N, 3, device=DEV)
+    rb.composite_rays(N, n_step, 1e-2, alive, rays_t, T(sig), T(rgb), deltas, ws, dep, img)
+    o_alive, o_t = np.arange(N, dtype=np.int32), nears.copy()
+    o_ws, o_dep, o_img = np.zeros(N, np.float32), np.zeros(N, np.float32), np.zeros((N, 3), np.float32)
+    orc.composite_rays(N, n_step, o_alive, o_t, sig, rgb, N_(deltas), o_ws, o_dep, o_img, 1e-2)
+    np.testing.assert_array_equal(N_(alive), o_alive)
+    np.testing.assert_allclose(N_(rays_t), o_t, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(N_(ws), o_ws, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N_(dep), o_dep, rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(N_(img), o_img, rtol=1e-4, atol=1e-5)
+
+    ref = refcuda.load("_raymarching")
+    if ref is not None:
+        x2, d2, dl2 = torch.zeros_like(xyzs), torch.zeros_like(dirs), torch.zeros_like(deltas)
+        ref.march_rays(N, n_step, torch.arange(N, dtype=torch.int32, device=DEV), T(nears), T(c["rays_o"]), T(c["rays_d"]),
+                       1.0, 0.0, 1024, 1, 128, T(c["bitfield"]), T(nears), T(fars), x2, d2, dl2, T(c["noises"]))
+        assert torch.equal(x2, xyzs) and torch.equal(dl2, deltas) and torch.equal(d2, dirs)
+
+
+GRID = [
+    dict(seed=31, B=1000, D=3, C=2, L=16, desired_resolution=2048, half=False),
+    dict(seed=32, B=1000, D=3, C=2, L=16, desired_resolution=32768, half=True),
+    dict(seed=33, B=500, D=2, C=4, L=4, desired_resolution=2048, half=False),
+    dict(seed=34, B=500, D=3, C=1, L=8, desired_resolution=512, half=False),
+    dict(seed=35, B=129, D=3, C=8, L=2, desired_resolution=64, half=True),
+]
+
+
+@pytest.mark.parametrize("cs", GRID, ids=lambda c: f"seed{c['seed']}")
+@pytest.mark.parametrize("layout", [0, 1])
+@pytest.mark.parametrize("interp", [0, 1])
+def test_grid_encode(be, orc, cs, layout, interp):
+    c = cases.grid_case(cs["seed"], cs["B"], cs["D"], cs["C"], cs["L"], 16, cs["desired_resolution"])
+    B, D, C, L = cs["B"], cs["D"], cs["C"], cs["L"]
+    dt = torch.half if cs["half"] else torch.float32
+    S = float(np.float32(np.log2(c["per_level_scale"])))
+    table_np = c["table"].astype(np.float16).astype(np.float32) if cs["half"] else c["table"]
+    emb = T(table_np).to(dt)
+    out = torch.empty((L, B, C) if layout == 0 else (B, L * C), device=DEV, dtype=dt)
+    dy = torch.empty(B, L * D * C, device=DEV, dtype=dt)
+    gb = be._gridencoder
+    gb.grid_encode_forward(T(c["inputs"]), emb, T(c["offsets"]), out, B, D, C, L, S, 16, dy, 0, False, interp,
+                           layout=layout)
+    # per-level scale as the DEVICE evaluates exp2f (see oracle/lnb_oracle.c)
+    ls = N_(torch.exp2(torch.arange(L, device=DEV, dtype=torch.float32) * torch.tensor(S, device=DEV)) * 16.0 - 1.0)
+    o_out, o_dy = orc.grid_encode_forward(c["inputs"], table_np, c["offsets"], c["per_level_scale"], 16, 0, False,
+                                          interp, cs["half"], True, ls)
+    got = N_(out) if layout == 1 else N_(out).transpose(1, 0, 2).reshape(B, L * C)
+    tol = dict(rtol=2e-3, atol=2e-3) if cs["half"] else dict(rtol=1e-4, atol=1e-5)
+    np.testing.assert_allclose(got, o_out, **tol)
+    assert (got[2] == 0).all() and (got[3] == 0).all(), "out-of-range inputs must encode to zero"
+    dtol = dict(rtol=5e-3, atol=0.5) if cs["half"] else dict(rtol=1e-3, atol=1e-2)
+    np.testing.assert_allclose(N_(dy), o_dy, **dtol)
+
+    rng = np.random.default_rng(cs["seed"] + 100)
+    g_np = (rng.normal(size=(B, L * C)) * 0.01).astype(np.float32)
+    if cs["half"]:
+        g_np = g_np.astype(np.float16).astype(np.float32)
+    g = T(g_np).to(dt) if layout == 1 else T(g_np.reshape(B, L, C).transpose(1, 0, 2)).to(dt)
+    gemb = torch.zeros_like(emb)
+    gin = torch.zeros(B, D, device=DEV, dtype=dt)
+    gb.grid_encode_backward(g.contiguous(), T(c["inputs"]), emb, T(c["offsets"]), gemb, B, D, C, L, S, 16, dy, gin, 0,
+                            False, interp, layout=layout)
+    o_gt, o_gi = orc.grid_encode_backward(g_np, c["inputs"], table_np.shape, c["offsets"], c["per_level_scale"], 16, 0,
+                                          False, interp, cs["half"], N_(dy), ls)
+    gtol = dict(rtol=2e-2, atol=2e-3) if cs["half"] else dict(rtol=1e-4, atol=1e-6)
+    np.testing.assert_allclose(N_(gemb), o_gt, **gtol)
+    itol = dict(rtol=2e-2, atol=5e-2) if cs["half"] else dict(rtol=1e-3, atol=1e-4)
+    np.testing.assert_allclose(N_(gin), o_gi, **itol)
+
+    ref = refcuda.load("_gridencoder")
+    if ref is not None and layout == 0:
+        out2, dy2 = torch.empty(L, B, C, device=DEV, dtype=dt), torch.empty_like(dy)
+        ref.grid_encode_forward(T(c["inputs"]), emb, T(c["offsets"]), out2, B, D, C, L, S, 16, dy2, 0, False, interp)
+        if cs["half"]:
+            np.testing.assert_allclose(N_(out), N_(out2), rtol=1e-3, atol=1e-3)
+        else:
+            np.testing.assert_allclose(N_(out), N_(out2), rtol=1e-5, atol=1e-6)
+        gemb2 = torch.zeros_like(emb)
+        gin2 = torch.zeros_like(gin)
+        ref.grid_encode_backward(g.contiguous(), T(c["inputs"]), emb, T(c["offsets"]), gemb2, B, D, C, L, S, 16, dy2,
+                                 gin2, 0, False, interp)
+        if not (cs["half"] and C == 1):  # the reference's half atomicAdd for C == 1 is an empty stub
+            np.testing.assert_allclose(N_(gemb), N_(gemb2), **gtol)
+
+
+def test_freq_encode(be, orc, golden_dir):
+    import os
+    g12 = np.load(os.path.join(golden_dir, "ref_py_freq_deg12.npz"))
+    x = g12["x"]
+    B = x.shape[0]
+    out = torch.empty(B, 75, device=DEV)
+    fb = be._freqencoder
+    fb.freq_encode_forward(T(x), B, 3, 12, 75, out)
+    # the reference's pure-torch encoder (exact sin/cos): __sinf on arguments up to 2^11 is only ~1e-3 accurate
+    np.testing.assert_allclose(N_(out)[:, :27], g12["y"][:, :27], rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(N_(out), g12["y"], rtol=0, atol=2e-3)
+    gi = torch.zeros(B, 3, device=DEV)
+    fb.freq_encode_backward(T(g12["g"]), out, B, 3, 12, 75, gi)
+    np.testing.assert_allclose(N_(gi), orc.freq_encode_backward(g12["g"], N_(out), 3, 12), rtol=1e-4, atol=1e-3)
+    ref = refcuda.load("_freqencoder")
+    if ref is not None:
+        out2, gi2 = torch.empty(B, 75, device=DEV), torch.zeros(B, 3, device=DEV)
+        ref.freq_encode_forward(T(x), B, 3, 12, 75, out2)
+        assert torch.equal(out, out2), "freq encoding must be bit-identical to the reference kernel"
+        ref.freq_encode_backward(T(g12["g"]), out2, B, 3, 12, 75, gi2)
+        np.testing.assert_allclose(N_(gi), N_(gi2), rtol=1e-5, atol=1e-4)
+
+
+@pytest.mark.parametrize("deg", [1, 2, 3, 4, 5, 6, 7, 8])
+def test_sh_encode(be, orc, deg):
+    rng = np.random.default_rng(42)
+    x = rng.uniform(-1, 1, size=(200, 3)).astype(np.float32)
+    x[:100] = cases.unit(x[:100])
+    out, dy = torch.empty(200, deg * deg, device=DEV), torch.empty(200, 3 * deg * deg, device=DEV)
+    sb = be._shencoder
+    sb.sh_encode_forward(T(x), out, 200, 3, deg, dy)
+    o_out, o_dy = orc.sh_encode_forward(x, deg, True)
+    np.testing.assert_allclose(N_(out), o_out, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(N_(dy), o_dy, rtol=1e-4, atol=2e-4)
+    g = rng.normal(size=(200, deg * deg)).astype(np.float32)
+    gi = torch.zeros(200, 3, device=DEV)
+    sb.sh_encode_backward(T(g), T(x), 200, 3, deg, dy, gi)
+    np.testing.assert_allclose(N_(gi), orc.sh_encode_backward(g, deg, N_(dy)), rtol=1e-4, atol=1e-4)
+    ref = refcuda.load("_shencoder")
+    if ref is not None:
+        out2, dy2 = torch.empty_like(out), torch.empty_like(dy)
+        ref.sh_encode_forward(T(x), out2, 200, 3, deg, dy2)
+        np.testing.assert_allclose(N_(out), N_(out2), rtol=1e-4, atol=2e-5)
+        np.testing.assert_allclose(N_(dy), N_(dy2), rtol=1e-4, atol=2e-4)
+
+
+FFMLP = [(256, 32, 2), (384, 96, 2), (128, 64, 3), (128 * 300, 32, 2), (128, 16, 2), (256, 128, 4)]
+
+
+@pytest.mark.parametrize("B,ind,nl", FFMLP)
+def test_ffmlp_forward_backward(be, orc, B, ind, nl):
+    c = cases.ffmlp_case(50, B, ind, 64, nl, 16)
+    x, w, g = T(c["x"]), T(c["w"]), T(c["g"])
+    fb = torch.empty(nl, B, 64, device=DEV, dtype=torch.half)
+    out = torch.empty(B, 16, device=DEV, dtype=torch.half)
+    mb = be._ffmlp
+    mb.ffmlp_forward(x, w, B, ind, 16, 64, nl, 0, 6, fb, out)
+    torch.cuda.synchronize()
+    o_out, o_fb = orc.ffmlp_forward(c["x"], c["w"], ind, 16, 64, nl)
+    np.testing.assert_allclose(N_(fb), o_fb, rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(N_(out), o_out, rtol=2e-3, atol=2e-3)
+
+    out_inf = torch.empty_like(out)
+    mb.ffmlp_inference(x, w, B, ind, 16, 64, nl, 0, 6, None, out_inf)
+    assert torch.equal(out, out_inf)
+
+    gi = torch.zeros(B, ind, device=DEV, dtype=torch.half)
+    gw = torch.zeros_like(w)
+    bb = torch.zeros(nl, B, 64, device=DEV, dtype=torch.half)
+    mb.ffmlp_backward(g, x, w, fb, B, ind, 16, 64, nl, 0, 6, True, bb, gi, gw)
+    torch.cuda.synchronize()
+    o_gi, o_gw, o_bb = orc.ffmlp_backward(c["g"], c["x"], c["w"], N_(fb), ind, 16, 64, nl, True)
+    np.testing.assert_allclose(N_(bb), o_bb, rtol=4e-3, atol=2e-3)
+    np.testing.assert_allclose(N_(gi), o_gi, rtol=4e-3, atol=2e-3)
+    scale = max(1.0, float(np.abs(o_gw).max()))
+    np.testing.assert_allclose(N_(gw), o_gw, rtol=4e-3, atol=2e-3 * scale)
+
+
+def test_ffmlp_rejects_unsupported_shapes(be):
+    x = torch.zeros(128, 32, device=DEV, dtype=torch.half)
+    w = torch.zeros(64 * (32 + 64 + 16), device=DEV, dtype=torch.half)
+    fb = torch.empty(2, 128, 64, device=DEV, dtype=torch.half)
+    out = torch.empty(128, 16, device=DEV, dtype=torch.half)
+    with pytest.raises(RuntimeError):
+        be._ffmlp.ffmlp_forward(x, w, 100, 32, 16, 64, 2, 0, 6, fb, out)      # B % 128 != 0
+    with pytest.raises(RuntimeError):
+        be._ffmlp.ffmlp_forward(x, w, 128, 32, 16, 32, 2, 0, 6, fb, out)      # hidden 32 not built
+    with pytest.raises(RuntimeError):
+        be._ffmlp.ffmlp_forward(x.float(), w, 128, 32, 16, 64, 2, 0, 6, fb, out)  # dtype
+
+
+def test_adam_step(be, orc):
+    rng = np.random.default_rng(7)
+    n = 100003
+    p, g = rng.normal(size=n).astype(np.float32), rng.normal(size=n).astype(np.float32)
+    m, v = np.zeros(n, np.float32), np.zeros(n, np.float32)
+    tp, tg, tm, tv = T(p), T(g), T(m), T(v)
+    th = torch.empty(n, device=DEV, dtype=torch.half)
+    for step in (1, 2, 3):
+        tg.copy_(T(g))
+        be.adam_step(tp, tg, tm, tv, th, 1e-2, 0.9, 0.99, 1e-15, step, grad_scale=0.5, zero_grad=True)
+        orc.adam_step(p, g, m, v, 1e-2, 0.9, 0.99, 1e-15, step, 0.5)
+    np.testing.assert_allclose(N_(tp), p, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(N_(tm), m, rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(N_(tv), v, rtol=1e-5, atol=1e-7)
+    assert float(tg.abs().max()) == 0.0
+    np.testing.assert_allclose(N_(th), p.astype(np.float16).astype(np.float32), rtol=1e-3, atol=1e-3)
