@@ -1,0 +1,410 @@
+#!/usr/bin/env python3
+"""Benchmark of the hot path: LiDAR-NeRF training rays/s on a synthetic 64x1024 panoramic sequence.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W]          our arm (one process per GPU under torchrun)
+    python bench.py --impl reference [...]                        the reference's algorithm on the host CPU cores
+
+A "step" is one optimiser step of the BASELINE.json configs[1] workload: 4096 rays per GPU -> occupancy-grid march
+(max_steps 1024, dt_gamma 0) -> hash grid L16 F2 T2^19 (res 16 -> 32768, fp16 table) -> FFMLP 64x2 density head
+-> freq(12) + geo -> FFMLP 64x2 LiDAR head -> compositing -> LiDAR loss -> backward -> Adam over all 13.7 M
+parameters, plus the density-grid refresh every 16 steps.  Prints ONE JSON line (see DESIGN.md section
+"Measurement" for every field).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "training rays/s (64x1024 pano)"
+WORKLOAD = ("KITTI-360-like synthetic 64x1024 pano x 8 frames, hashgrid L16 F2 T2^19 res16->32768 + ffmlp 64x2 sigma "
+            "+ ffmlp 64x2 lidar head, 4096 rays/GPU/step, occupancy march max_steps=1024 dt_gamma=0, "
+            "fwd+bwd+Adam(13.7M params)+grid refresh/16 steps")
+RAYS = 4096
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=64)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rays", type=int, default=RAYS)
+    ap.add_argument("--frames", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-profile", action="store_true")
+    ap.add_argument("--cpu-rays", type=int, default=512, help="rays per CPU-baseline step (bounded sample)")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for k, name in enumerate(names):
+                if f[5 + k].lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------------------------
+def make_pool(seq, n_rays, n_batches, seed, device):
+    import torch
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    pool = []
+    for b in range(n_batches):
+        ro, rd, gt = seq.sample_batch(n_rays, frame=b % seq.n_frames, generator=gen, device=device)
+        pool.append(torch.cat([ro, rd, gt], dim=1).contiguous())     # [N, 9]: one buffer per batch
+    return pool
+
+
+def cpu_reference_leg(args, threads, rays, steps):
+    """The reference's algorithm for this path on the host cores (oracle port), on a bounded sample of the workload."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc, field_step as fs
+    from lidar_nerf_b200.nerf.engine import FieldConfig
+    from lidar_nerf_b200.data.synthetic import SyntheticLidarSequence
+    orc.build()
+    orc.set_threads(threads)
+    torch.set_num_threads(threads)
+    cfg = FieldConfig()
+    seq = SyntheticLidarSequence(n_frames=2, device="cpu")
+    rng = np.random.default_rng(0)
+    params = fs.FieldParams(cfg)
+    params.P[:params.n_table] = rng.uniform(-1e-4, 1e-4, params.n_table).astype(np.float32)
+    params.P[params.n_table:] = rng.uniform(-0.2165, 0.2165, params.n_sigma + params.n_head).astype(np.float32)
+    # occupancy prior from the GT returns (same construction as the GPU arm)
+    pts = seq.surface_points().numpy()
+    H = cfg.grid_size
+    cell = np.clip((0.5 * (pts / cfg.bound + 1) * H).astype(np.int64), 0, H - 1)
+    offs = np.stack(np.meshgrid(*([np.arange(-1, 2)] * 3), indexing="ij"), -1).reshape(-1, 3)
+    cell = np.unique(np.clip(cell[:, None, :] + offs[None], 0, H - 1).reshape(-1, 3), axis=0)
+    bits = np.zeros(H ** 3, bool)
+    bits[orc.morton3D(cell.astype(np.int32)).astype(np.int64)] = True
+    bitfield = np.packbits(bits.reshape(-1, 8), axis=1, bitorder="little").reshape(-1)
+    gen = torch.Generator().manual_seed(0)
+    times, n_samples = [], 0
+    for s in range(steps + 1):
+        ro, rd, gt = seq.sample_batch(rays, frame=s % 2, generator=gen)
+        noises = rng.uniform(0, 1, rays).astype(np.float32)
+        t = time.perf_counter()
+        out = fs.field_step(params, ro.numpy(), rd.numpy(), gt.numpy(), noises, bitfield, rays * 64)
+        dt = time.perf_counter() - t
+        if s > 0:   # first step warms caches / page-faults the 55 MB table
+            times.append(dt)
+            n_samples = out["n_samples"]
+    med = sorted(times)[len(times) // 2]
+    return {"value": rays / med, "unit": "rays/s", "cores": threads, "kind": "port",
+            "sample": f"{steps} steps x {rays} rays ({n_samples} samples/step) of the same workload incl. Adam over the "
+                      f"full 13.7M-parameter table; median step {med * 1e3:.1f} ms"}, med
+
+
+# --------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        threads = os.cpu_count() or 1
+        cb, med = cpu_reference_leg(args, threads, args.cpu_rays, max(args.steps if args.steps < 8 else 5, 2))
+        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": med * 1e3, "higher_is_better": True,
+               "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16-rounded tables/MLP) on CPU", "data": "synthetic",
+               "config": {"workload": WORKLOAD, "note": "reference algorithm on host CPU cores (oracle port; the "
+                          "reference's own CUDA/Python path cannot travel to this box)"},
+               "cpu_baseline": cb,
+               "e2e": {"value": cb["value"], "unit": "rays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from lidar_nerf_b200 import _lib
+    from lidar_nerf_b200.nerf.engine import LidarFieldEngine, FieldConfig
+    from lidar_nerf_b200.data.synthetic import SyntheticLidarSequence
+
+    torch.cuda.set_device(local)
+    dev = torch.device(f"cuda:{local}")
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    N = args.rays
+    cfg = FieldConfig()
+    seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
+    eng = LidarFieldEngine(cfg, N, device=dev, sample_budget=N * 64)
+    eng.seed_occupancy_from_points(seq.surface_points())
+    pool = make_pool(seq, N, 32, seed=1000 + rank, device=dev)
+    pool_host = [b.cpu().pin_memory() for b in pool]
+
+    def load(b):
+        eng.rays_o.copy_(b[:, 0:3], non_blocking=True)
+        eng.rays_d.copy_(b[:, 3:6], non_blocking=True)
+        eng.gt.copy_(b[:, 6:9], non_blocking=True)
+
+    # ---- untimed preparation: size the sample budget from real counts, refresh the grid once, capture the graph ----
+    cfg_interval = cfg.grid_update_interval
+    cfg.grid_update_interval = 0
+    for i in range(3):
+        load(pool[i])
+        eng.train_step(use_graph=False)
+        eng.fit_sample_budget()
+    eng.update_density_grid(full=True)
+    load(pool[0])
+    eng.train_step(use_graph=False)
+    eng.fit_sample_budget(headroom=1.25)
+    cfg.grid_update_interval = cfg_interval
+    eng.step_count = 17 * cfg_interval      # steady state: partial grid refreshes
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(steps, host):
+        staging = torch.empty(N, 9, device=dev)
+        for i in range(steps):
+            if host:
+                staging.copy_(pool_host[i % len(pool_host)], non_blocking=True)
+                load(staging)
+            else:
+                load(pool[i % len(pool)])
+            eng.train_step()
+            if host:
+                eng.read_loss()           # D2H read of the step's loss
+
+    run(args.warmup, False)
+    launches0 = _lib.launch_count()
+    clocks = ClockSampler(local)
+    barrier()
+    clocks.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(args.steps, False)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.launch_count() - launches0
+    produced, _ = eng.samples_last_step()
+
+    # ---- end to end through the host boundary ----
+    run(2, True)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    run(args.steps, True)
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    clk = clocks.stop()
+
+    t = torch.tensor([ms, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+
+    # ---- per-kernel device times (eager pass, CUDA events on the launching stream) -> roofline of the dominant one ----
+    roof, kernels = None, None
+    if rank == 0 and not args.no_profile:
+        kernels, roof = profile_kernels(eng, pool, load)
+
+    if rank == 0:
+        value = world * N * args.steps / (ms * 1e-3)
+        out = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+               "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+               "vs_baseline": None, "dtype": "f16 tables+MLP (fp32 accumulate) / f32 march+composite+Adam",
+               "data": "synthetic",
+               "config": {"workload": WORKLOAD, "rays_per_gpu": N, "samples_per_step": produced,
+                          "samples_per_ray": produced / N, "sample_budget_M": eng.M, "params": eng.n_params,
+                          "l2": "each step streams the 383 MB Adam state (> 126 MB L2); no explicit flush",
+                          "parallelism": f"dp{world} (NCCL allreduce of the flat fp32 gradient)" if world > 1 else "single"},
+               "clocks": clk,
+               "e2e": {"value": world * N * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
+                       "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4},
+               "gpu_launches": int(launches)}
+        if roof:
+            out["roofline"] = roof
+            out["kernels_us"] = kernels
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_reference_leg(args, 1, args.cpu_rays, args.cpu_steps)
+            out["cpu_baseline"] = cb
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def profile_kernels(eng, pool, load, iters=5):
+    """Time every kernel of one step with CUDA events by running the step eagerly with event pairs injected
+    around each C-ABI call (the calls are looked up by name on the backend objects)."""
+    import torch
+    from lidar_nerf_b200 import backend as be
+    from lidar_nerf_b200.nerf import engine as E
+    times = {}
+    order = []
+
+    def wrap(obj, name, label):
+        fn = getattr(obj, name)
+
+        def timed(*a, **k):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **k)
+            e.record()
+            times.setdefault(label, []).append((s, e))
+            if label not in order:
+                order.append(label)
+            return r
+        setattr(obj, name, timed)
+        return fn
+
+    saved = []
+    for obj, name in ((E.rm, "march_rays_train"), (E.rm, "composite_rays_train_forward_ex"),
+                      (E.rm, "composite_rays_train_backward_ex"), (E.ff, "ffmlp_forward")):
+        saved.append((obj, name, wrap(obj, name, name)))
+    lib_names = ["lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
+                 "lnb_lidar_loss", "lnb_field_head_out_grad", "lnb_ffmlp_backward_accumulate", "lnb_field_sigma_out_grad",
+                 "lnb_grid_encode_backward_ex"]
+
+    class LibProxy:
+        def __init__(self, real):
+            self._real = real
+
+        def __getattr__(self, n):
+            fn = getattr(self._real, n)
+            if n not in lib_names:
+                return fn
+
+            def timed(*a):
+                s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                s.record()
+                r = fn(*a)
+                e.record()
+                times.setdefault(n, []).append((s, e))
+                if n not in order:
+                    order.append(n)
+                return r
+            return timed
+
+    real_lib, real_adam = E.lib, E.adam_step
+    E.lib = LibProxy(real_lib)
+
+    def adam_timed(*a, **k):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        real_adam(*a, **k)
+        e.record()
+        times.setdefault("lnb_adam_step", []).append((s, e))
+        if "lnb_adam_step" not in order:
+            order.append("lnb_adam_step")
+    E.adam_step = adam_timed
+    interval = eng.cfg.grid_update_interval
+    eng.cfg.grid_update_interval = 0
+    try:
+        for i in range(iters + 1):
+            load(pool[i % len(pool)])
+            eng.train_step(use_graph=False)
+        torch.cuda.synchronize()
+    finally:
+        for obj, name, fn in saved:
+            setattr(obj, name, fn)
+        E.lib, E.adam_step = real_lib, real_adam
+        eng.cfg.grid_update_interval = interval
+    us = {}
+    for label in order:
+        pairs = times[label]
+        per_call = [s.elapsed_time(e) * 1e3 for s, e in pairs]
+        calls_per_step = len(pairs) // (iters + 1)
+        per_call = per_call[calls_per_step:]   # drop the first (cold) iteration
+        us[label] = {"us_per_step": sum(per_call) / iters, "launches_per_step": calls_per_step}
+    produced, _ = eng.samples_last_step()
+    top = max(us, key=lambda k: us[k]["us_per_step"])
+    hbm, how = peaks()
+    c = eng.cfg
+    per_sample_fwd = c.num_levels * 8 * c.level_dim * 2                   # 512 B: L x 2^D corners x F x fp16
+    alg = {
+        "lnb_adam_step": (eng.n_params * 34, "34 B/param: p,g,m,v read (16) + p,m,v,g=0 write (16) + fp16 shadow (2)"),
+        "lnb_grid_encode_forward_ex": (eng.M * (per_sample_fwd + 12 + c.num_levels * c.level_dim * 2),
+                                       "per sample 512 B gathers + 12 B xyz + 64 B features out"),
+        "lnb_grid_encode_backward_ex": (eng.M * (2 * c.num_levels * 8 * c.level_dim * 4 + 12 + 64),
+                                        "per sample 16x8 fp32x2 read-modify-write (2048 B) + 12 B xyz + 64 B grad in"),
+        "lnb_ffmlp_backward_accumulate": (eng.M * (32 + 192 + 2 * 128 + 192 + 64 + 2 * 128 + 64) // 2,
+                                          "per sample grad in + inputs + saved activations read, grad_inputs written (avg of both MLPs)"),
+        "ffmlp_forward": (eng.M * ((64 + 32 + 2 * 128) + (192 + 32 + 2 * 128)) // 2,
+                          "per sample inputs + outputs + 2 saved activation rows (avg of both MLPs)"),
+    }
+    launches = us[top]["launches_per_step"]
+    dur_s = us[top]["us_per_step"] / max(launches, 1) * 1e-6
+    if top in alg:
+        nbytes, how_b = alg[top]
+        ach = nbytes / dur_s / 1e9
+        roof = {"bound": "hbm", "kernel": top, "achieved": ach, "peak": hbm, "unit": "GB/s", "frac": ach / hbm,
+                "traffic": None, "algorithmic_bytes_per_launch": nbytes, "bytes_model": how_b,
+                "avg_launch_us": dur_s * 1e6, "peak_source": how, "samples_per_launch": eng.M}
+    else:
+        roof = {"bound": "hbm", "kernel": top, "achieved": None, "peak": hbm, "unit": "GB/s", "frac": None,
+                "traffic": None, "avg_launch_us": dur_s * 1e6, "peak_source": how}
+    return us, roof
+
+
+if __name__ == "__main__":
+    sys.exit(main())

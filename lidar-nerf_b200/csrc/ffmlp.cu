@@ -228,131 +228,179 @@ k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t
 // =====================================================================================================
 // backward
 // =====================================================================================================
-// TMEM columns: [0,64) dgrad accumulator, [64,128) dW_out^T, [128 + 64 l) dW_hid[l], then dW_in per k-tile.
-__global__ void __launch_bounds__(kThreads)
+// Warp-specialised: two compute warpgroups (128 threads each, one 128-row tile in flight each) + one MMA warp
+// whose lane 0 issues EVERY tcgen05.mma of the CTA (so all accumulations into the shared weight-gradient
+// accumulators are ordered on the tensor pipe).  A warpgroup loads all inputs of its tile at once
+// (G, every saved activation, X), then walks the layers: [operands ready] -> MMA warp -> [accumulator ready] ->
+// epilogue (ReLU mask, fp16) -> next layer's operand.  While one warpgroup waits on memory or the tensor core,
+// the other runs its epilogue.
+//
+// TMEM columns: [0,64) / [64,128) dgrad accumulators of warpgroup 0 / 1; then dW_out^T (64), dW_hid[l] (64 each),
+// dW_in per 64-column input tile (64 each) - accumulated over ALL tiles of the CTA, flushed once at the end.
+constexpr uint32_t kWG = 2;
+constexpr uint32_t kBwdThreads = kWG * 128 + 32;
+
+__device__ __forceinline__ void wg_sync(uint32_t wg) {
+    asm volatile("bar.sync %0, 128;" ::"r"(wg + 1) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
+// cooperative movers for ONE warpgroup (128 threads, tid = thread index inside the group)
+__device__ __forceinline__ void wg_load_tiles(uint32_t tid, uint32_t tile0, const __half *__restrict__ src,
+                                              uint32_t cols, uint32_t ld) {
+    const uint32_t kt = (cols + 63) / 64;
+    const uint32_t cpr = kt * 8;
+    for (uint32_t q = tid; q < kRows * cpr; q += 128) {
+        const uint32_t r = q / cpr, c = q - r * cpr;
+        if (c * 8 < cols) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld + c * 8));
+            sts128(tile_chunk_addr(tile0 + (c >> 3) * kTileBytes, r, c & 7), v);
+        }
+    }
+}
+__device__ __forceinline__ void wg_store_tile_rows(uint32_t tid, uint32_t tile, __half *__restrict__ dst) {
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+        const uint32_t q = tid + j * 128;
+        const uint32_t r = q >> 3, c = q & 7;
+        *reinterpret_cast<uint4 *>(dst + (size_t)r * 64 + c * 8) = lds128(tile_chunk_addr(tile, r, c));
+    }
+}
+
+__global__ void __launch_bounds__(kBwdThreads, 1)
 k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __half *__restrict__ W,
             const __half *__restrict__ fbuf, uint32_t B, Shape sh, __half *__restrict__ bbuf,
             __half *__restrict__ dX, float *__restrict__ wgrad /* fp32, flat weight layout */) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t n_act = sh.n_hid + 1;                                  // saved activation tiles per row tile
     const uint32_t s_win = sbase;
     const uint32_t s_whid = s_win + sh.kt_in * kWTileBytes;
     const uint32_t s_wout = s_whid + sh.n_hid * kWTileBytes;
-    const uint32_t s_x = s_wout + 2048;
-    const uint32_t s_h = s_x + sh.kt_in * kTileBytes;   // saved activation of the current layer
-    const uint32_t s_d = s_h + kTileBytes;              // d(pre-activation) of the current layer
-    const uint32_t s_g = s_d + kTileBytes;              // upstream gradient tile (cols >= 16 stay zero)
-    const uint32_t s_bar = s_g + kTileBytes;
-    const uint32_t s_slot = s_bar + 8;
+    const uint32_t wg_bytes = (2 + n_act + sh.kt_in) * kTileBytes;        // G, dH, activations, X
+    const uint32_t s_wg0 = s_wout + 2048;
+    const uint32_t s_bar = s_wg0 + kWG * wg_bytes;                        // ready[2], done[2], fin, slot
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t row = threadIdx.x;
+    const uint32_t wg = threadIdx.x >> 7;                                 // 0,1 compute; 2 = MMA warp
+    const uint32_t tid = threadIdx.x & 127;
+    const uint32_t bar_ready0 = s_bar, bar_done0 = s_bar + 16, bar_fin = s_bar + 32, s_slot = s_bar + 40;
 
-    if (warp == 0) tmem_alloc(s_slot, 512);
-    if (threadIdx.x == 32) {
-        mbar_init(s_bar, 1);
+    if (warp == kWG * 4) tmem_alloc(s_slot, 512);
+    if (threadIdx.x == 0) {
+        for (uint32_t g = 0; g < kWG; ++g) {
+            mbar_init(bar_ready0 + 8 * g, 128);
+            mbar_init(bar_done0 + 8 * g, 1);
+        }
+        mbar_init(bar_fin, 1);
         mbar_init_fence();
     }
-    load_tiles(s_win, kWTileBytes, W, kHid, sh.in_dim, sh.in_dim, true);
-    for (uint32_t l = 0; l < sh.n_hid; ++l)
-        load_tiles(s_whid + l * kWTileBytes, kWTileBytes, W + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
-                   kHid, false);
-    load_tiles(s_wout, kWOutBytes, W + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid, false);
-    // zero the gradient tile and the input tiles once: their padding columns are read by N = 64 wgrad MMAs
-    for (uint32_t q = threadIdx.x; q < kRows * 8; q += kThreads) sts128(s_g + q * 16, make_uint4(0, 0, 0, 0));
-    for (uint32_t q = threadIdx.x; q < sh.kt_in * kRows * 8; q += kThreads) sts128(s_x + q * 16, make_uint4(0, 0, 0, 0));
+    // weights (all threads), zero padding of the per-group G and X tiles (their padding columns are read by N = 64 MMAs)
+    {
+        const uint32_t nthr = kBwdThreads, t = threadIdx.x;
+        auto load_w = [&](uint32_t tile0, uint32_t stride, const __half *src, uint32_t rows, uint32_t cols, uint32_t ld) {
+            const uint32_t kt = (cols + 63) / 64, cpr = kt * 8;
+            for (uint32_t q = t; q < rows * cpr; q += nthr) {
+                const uint32_t r = q / cpr, c = q - r * cpr;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (c * 8 < cols) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld + c * 8));
+                sts128(tile_chunk_addr(tile0 + (c >> 3) * stride, r, c & 7), v);
+            }
+        };
+        load_w(s_win, kWTileBytes, W, kHid, sh.in_dim, sh.in_dim);
+        for (uint32_t l = 0; l < sh.n_hid; ++l)
+            load_w(s_whid + l * kWTileBytes, kWTileBytes, W + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid);
+        load_w(s_wout, kWOutBytes, W + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid);
+        for (uint32_t q = t; q < kWG * wg_bytes / 16; q += nthr) sts128(s_wg0 + q * 16, make_uint4(0, 0, 0, 0));
+    }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     fence_after_sync();
     const uint32_t tmem = lds32(s_slot);
-    const uint32_t d_acc = tmem;
-    const uint32_t d_wout = tmem + 64;
-    const uint32_t d_whid = tmem + 128;
+    const uint32_t d_wout = tmem + 128;
+    const uint32_t d_whid = tmem + 192;
     const uint32_t d_win = d_whid + 64 * sh.n_hid;
-    const uint32_t lane_sel = (warp * 32u) << 16;
 
-    uint32_t phase = 0;
     const uint32_t n_tiles = B / kRows;
-    uint32_t iter = 0;
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++iter) {
-        const size_t row0 = (size_t)tile * kRows;
-        const bool acc = iter > 0;
+    const uint32_t stride_tiles = gridDim.x * kWG;
+    const uint32_t n_iter = (n_tiles + stride_tiles - 1) / stride_tiles;
+    const bool want_dx = dX != nullptr;
+    const uint32_t extra_dx = (want_dx && sh.kt_in > 1) ? sh.kt_in - 1 : 0;
 
-        // ---- output layer: dH_last = G W_out ; dW_out^T += H_last^T G ----
-        // G tile: 16 valid columns = chunks 0,1 of every row
-        for (uint32_t q = threadIdx.x; q < kRows * 2; q += kThreads) {
-            const uint32_t r = q >> 1, c = q & 1;
-            sts128(tile_chunk_addr(s_g, r, c), __ldg(reinterpret_cast<const uint4 *>(G + (row0 + r) * kOut + c * 8)));
-        }
-        load_tiles(s_h, kTileBytes, fbuf + ((size_t)sh.n_hid * B + row0) * kHid, kRows, kHid, kHid, false);
-        fence_proxy_async();
-        fence_before_sync();
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            fence_after_sync();
-            issue_dgrad(d_acc, s_g, s_wout, 1);            // K = 16 output channels
-            issue_wgrad(d_wout, s_h, s_g, acc);             // rows: hidden unit j, cols: output o (>=16 zero)
-            mma_commit(s_bar);
-        }
-
-        // ---- hidden layers, last to first ----
-        for (int layer = (int)sh.n_hid; layer >= 0; --layer) {
-            mbar_wait(s_bar, phase);
-            phase ^= 1;
-            fence_after_sync();
-            // epilogue: d(pre-act) = acc * (saved activation > 0)  -> s_d  (this thread's row)
-#pragma unroll
-            for (uint32_t half_id = 0; half_id < 2; ++half_id) {
-                uint32_t v[32];
-                tmem_ld32(d_acc + lane_sel + half_id * 32, v);
-                tmem_ld_wait();
-#pragma unroll
-                for (uint32_t c = 0; c < 4; ++c) {
-                    const uint4 hv = lds128(tile_chunk_addr(s_h, row, half_id * 4 + c));
-                    const __half2 *hh = reinterpret_cast<const __half2 *>(&hv);
-                    uint32_t pk[4];
-#pragma unroll
-                    for (uint32_t e = 0; e < 4; ++e) {
-                        const float2 act = __half22float2(hh[e]);
-                        const float a = act.x > 0.f ? __uint_as_float(v[c * 8 + 2 * e]) : 0.f;
-                        const float b = act.y > 0.f ? __uint_as_float(v[c * 8 + 2 * e + 1]) : 0.f;
-                        pk[e] = pack_half2(a, b);
+    if (wg == kWG) {
+        // ================= MMA warp =================
+        if (lane == 0) {
+            uint32_t par_ready[kWG] = {0, 0};
+            for (uint32_t it = 0; it < n_iter; ++it) {
+                const uint32_t n_phase = 2 + sh.n_hid + extra_dx;
+                for (uint32_t ph = 0; ph < n_phase; ++ph) {
+                    for (uint32_t g = 0; g < kWG; ++g) {
+                        const uint32_t tile = (it * gridDim.x + blockIdx.x) * kWG + g;
+                        if (tile >= n_tiles) continue;
+                        const uint32_t base = s_wg0 + g * wg_bytes;
+                        const uint32_t s_g = base, s_d = base + kTileBytes, s_h = base + 2 * kTileBytes;
+                        const uint32_t s_x = s_h + n_act * kTileBytes;
+                        const uint32_t d_acc = tmem + 64 * g;
+                        mbar_wait(bar_ready0 + 8 * g, par_ready[g]);
+                        par_ready[g] ^= 1;
+                        fence_after_sync();
+                        // group 0 always owns a tile in iteration 0 and is served first: it initialises the accumulators
+                        const bool accw = !(it == 0 && g == 0);
+                        if (ph == 0) {
+                            issue_dgrad(d_acc, s_g, s_wout, 1);
+                            issue_wgrad(d_wout, s_h + sh.n_hid * kTileBytes, s_g, accw);
+                        } else if (ph <= sh.n_hid) {
+                            const uint32_t layer = sh.n_hid - ph + 1;        // dpre of h_layer is in s_d
+                            issue_dgrad(d_acc, s_d, s_whid + (layer - 1) * kWTileBytes, 4);
+                            issue_wgrad(d_whid + 64 * (layer - 1), s_d, s_h + (layer - 1) * kTileBytes, accw);
+                        } else if (ph == sh.n_hid + 1) {
+                            for (uint32_t t = 0; t < sh.kt_in; ++t) issue_wgrad(d_win + 64 * t, s_d, s_x + t * kTileBytes, accw);
+                            if (want_dx) issue_dgrad(d_acc, s_d, s_win, 4);
+                        } else {
+                            const uint32_t t = ph - sh.n_hid - 1;            // 1 .. kt_in-1
+                            issue_dgrad(d_acc, s_d, s_win + t * kWTileBytes, 4);
+                        }
+                        mma_commit(bar_done0 + 8 * g);
                     }
-                    sts128(tile_chunk_addr(s_d, row, half_id * 4 + c), make_uint4(pk[0], pk[1], pk[2], pk[3]));
                 }
             }
-            __syncthreads();  // all rows of s_h consumed (mask) and s_d written before s_h is reloaded
-            if (layer > 0) {
-                load_tiles(s_h, kTileBytes, fbuf + ((size_t)(layer - 1) * B + row0) * kHid, kRows, kHid, kHid, false);
-            } else {
-                load_tiles(s_x, kTileBytes, X + row0 * sh.in_dim, kRows, sh.in_dim, sh.in_dim, false);
+            mma_commit(bar_fin);
+        }
+    } else {
+        // ================= compute warpgroups =================
+        const uint32_t base = s_wg0 + wg * wg_bytes;
+        const uint32_t s_g = base, s_d = base + kTileBytes, s_h = base + 2 * kTileBytes;
+        const uint32_t s_x = s_h + n_act * kTileBytes;
+        const uint32_t d_acc = tmem + 64 * wg;
+        const uint32_t bar_ready = bar_ready0 + 8 * wg, bar_done = bar_done0 + 8 * wg;
+        const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
+        const uint32_t row = tid;
+        uint32_t par_done = 0;
+        for (uint32_t it = 0; it < n_iter; ++it) {
+            const uint32_t tile = (it * gridDim.x + blockIdx.x) * kWG + wg;
+            if (tile >= n_tiles) break;
+            const size_t row0 = (size_t)tile * kRows;
+            // ---- all inputs of this tile at once ----
+            for (uint32_t q = tid; q < kRows * 2; q += 128) {
+                const uint32_t r = q >> 1, c = q & 1;
+                sts128(tile_chunk_addr(s_g, r, c), __ldg(reinterpret_cast<const uint4 *>(G + (row0 + r) * kOut + c * 8)));
             }
+            for (uint32_t l = 0; l < n_act; ++l)
+                wg_load_tiles(tid, s_h + l * kTileBytes, fbuf + ((size_t)l * B + row0) * kHid, kHid, kHid);
+            wg_load_tiles(tid, s_x, X + row0 * sh.in_dim, sh.in_dim, sh.in_dim);
             fence_proxy_async();
             fence_before_sync();
-            __syncthreads();
-            if (threadIdx.x == 0) {
-                fence_after_sync();
-                if (layer > 0) {
-                    issue_dgrad(d_acc, s_d, s_whid + (layer - 1) * kWTileBytes, 4);   // dH_{l-1} = dpre_l W_l
-                    issue_wgrad(d_whid + 64 * (layer - 1), s_d, s_h, acc);          // dW_l += dpre_l^T H_{l-1}
-                } else {
-                    for (uint32_t t = 0; t < sh.kt_in; ++t)
-                        issue_wgrad(d_win + 64 * t, s_d, s_x + t * kTileBytes, acc);  // dW_in += dpre_0^T X
-                    if (dX) issue_dgrad(d_acc, s_d, s_win, 4);                       // dX[:, 0:64]
-                }
-                mma_commit(s_bar);
-            }
-            if (bbuf) store_tile_rows(s_d, bbuf + ((size_t)(sh.n_hid - layer) * B + row0) * kHid);
-        }
+            mbar_arrive(bar_ready);
 
-        // ---- input gradient, 64 columns at a time ----
-        for (uint32_t t = 0; t < sh.kt_in; ++t) {
-            mbar_wait(s_bar, phase);
-            phase ^= 1;
-            fence_after_sync();
-            if (dX) {
-                const uint32_t cols = min(64u, sh.in_dim - t * 64);
+            // ---- layers, last to first: epilogue = mask with the saved activation, fp16, operand for the next MMA ----
+            for (int layer = (int)sh.n_hid; layer >= 0; --layer) {
+                mbar_wait(bar_done, par_done);
+                par_done ^= 1;
+                fence_after_sync();
+                const uint32_t s_act = s_h + (uint32_t)layer * kTileBytes;
 #pragma unroll
                 for (uint32_t half_id = 0; half_id < 2; ++half_id) {
                     uint32_t v[32];
@@ -360,77 +408,114 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
                     tmem_ld_wait();
 #pragma unroll
                     for (uint32_t c = 0; c < 4; ++c) {
-                        const uint32_t col = half_id * 32 + c * 8;
-                        if (col < cols) {
-                            uint4 pk;
-                            pk.x = pack_half2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
-                            pk.y = pack_half2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
-                            pk.z = pack_half2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
-                            pk.w = pack_half2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
-                            *reinterpret_cast<uint4 *>(dX + (row0 + row) * sh.in_dim + t * 64 + col) = pk;
+                        const uint4 hv = lds128(tile_chunk_addr(s_act, row, half_id * 4 + c));
+                        const __half2 *hh = reinterpret_cast<const __half2 *>(&hv);
+                        uint32_t pk[4];
+#pragma unroll
+                        for (uint32_t e = 0; e < 4; ++e) {
+                            const float2 act = __half22float2(hh[e]);
+                            const float a = act.x > 0.f ? __uint_as_float(v[c * 8 + 2 * e]) : 0.f;
+                            const float b = act.y > 0.f ? __uint_as_float(v[c * 8 + 2 * e + 1]) : 0.f;
+                            pk[e] = pack_half2(a, b);
+                        }
+                        sts128(tile_chunk_addr(s_d, row, half_id * 4 + c), make_uint4(pk[0], pk[1], pk[2], pk[3]));
+                    }
+                }
+                fence_proxy_async();
+                fence_before_sync();
+                mbar_arrive(bar_ready);
+                if (bbuf) {
+                    wg_sync(wg);   // every row of s_d written
+                    wg_store_tile_rows(tid, s_d, bbuf + ((size_t)(sh.n_hid - layer) * B + row0) * kHid);
+                    wg_sync(wg);   // all readers done before the next epilogue rewrites s_d
+                }
+            }
+            // ---- input-gradient tiles ----
+            for (uint32_t t = 0; t < sh.kt_in; ++t) {
+                if (t > 0 && !want_dx) break;
+                mbar_wait(bar_done, par_done);
+                par_done ^= 1;
+                fence_after_sync();
+                if (want_dx) {
+                    const uint32_t cols = min(64u, sh.in_dim - t * 64);
+#pragma unroll
+                    for (uint32_t half_id = 0; half_id < 2; ++half_id) {
+                        uint32_t v[32];
+                        tmem_ld32(d_acc + lane_sel + half_id * 32, v);
+                        tmem_ld_wait();
+#pragma unroll
+                        for (uint32_t c = 0; c < 4; ++c) {
+                            const uint32_t col = half_id * 32 + c * 8;
+                            if (col < cols) {
+                                uint4 pk;
+                                pk.x = pack_half2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
+                                pk.y = pack_half2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
+                                pk.z = pack_half2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
+                                pk.w = pack_half2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
+                                *reinterpret_cast<uint4 *>(dX + (row0 + row) * sh.in_dim + t * 64 + col) = pk;
+                            }
                         }
                     }
                 }
-            }
-            fence_before_sync();
-            __syncthreads();
-            if (t + 1 < sh.kt_in) {
-                if (threadIdx.x == 0) {
-                    fence_after_sync();
-                    if (dX) issue_dgrad(d_acc, s_d, s_win + (t + 1) * kWTileBytes, 4);
-                    mma_commit(s_bar);
+                if (t + 1 < sh.kt_in && want_dx) {
+                    fence_before_sync();
+                    mbar_arrive(bar_ready);   // accumulator drained -> next 64 input columns
                 }
             }
+            // the next tile's loads overwrite G / activations / X: every MMA that read them has completed
+            // (the last `done` wait above covers all MMAs issued for this tile)
+            wg_sync(wg);
         }
     }
 
     // ---- flush the tensor-memory weight-gradient accumulators (fp32 atomics into the flat layout) ----
-    // UMMA M = 64 puts row m at TMEM lane (m / 16) * 32 + m % 16: warp w, lanes 0..15 own rows 16 w + lane.
-    fence_before_sync();
-    __syncthreads();
-    fence_after_sync();
-    if (iter > 0) {
-        const uint32_t m = warp * 16 + lane;  // valid when lane < 16
-        float *w_in = wgrad;
-        float *w_hid = wgrad + sh.w_in_elems;
-        float *w_out = w_hid + (size_t)sh.n_hid * kHid * kHid;
-        // dW_out^T : row = hidden j, col = output o
-        {
-            uint32_t v[16];
-            tmem_ld16(d_wout + lane_sel, v);
-            tmem_ld_wait();
-            if (lane < 16)
+    // UMMA M = 64 puts row m at TMEM lane (m / 16) * 32 + m % 16: warp w (mod 4), lanes 0..15 own rows 16 (w%4) + lane.
+    if (wg == 0) {
+        mbar_wait(bar_fin, 0);
+        fence_after_sync();
+        if (blockIdx.x * kWG < n_tiles) {
+            const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
+            const uint32_t m = (warp & 3u) * 16 + lane;  // valid when lane < 16
+            float *w_in = wgrad;
+            float *w_hid = wgrad + sh.w_in_elems;
+            float *w_out = w_hid + (size_t)sh.n_hid * kHid * kHid;
+            {
+                uint32_t v[16];
+                tmem_ld16(d_wout + lane_sel, v);
+                tmem_ld_wait();
+                if (lane < 16)
 #pragma unroll
-                for (uint32_t o = 0; o < 16; ++o) atomicAdd(w_out + o * kHid + m, __uint_as_float(v[o]));
+                    for (uint32_t o = 0; o < 16; ++o) atomicAdd(w_out + o * kHid + m, __uint_as_float(v[o]));
+            }
+            for (uint32_t l = 0; l < sh.n_hid; ++l)
+#pragma unroll
+                for (uint32_t half_id = 0; half_id < 2; ++half_id) {
+                    uint32_t v[32];
+                    tmem_ld32(d_whid + 64 * l + lane_sel + half_id * 32, v);
+                    tmem_ld_wait();
+                    if (lane < 16)
+#pragma unroll
+                        for (uint32_t n = 0; n < 32; ++n)
+                            atomicAdd(w_hid + (size_t)l * kHid * kHid + m * kHid + half_id * 32 + n, __uint_as_float(v[n]));
+                }
+            for (uint32_t t = 0; t < sh.kt_in; ++t)
+#pragma unroll
+                for (uint32_t half_id = 0; half_id < 2; ++half_id) {
+                    uint32_t v[32];
+                    tmem_ld32(d_win + 64 * t + lane_sel + half_id * 32, v);
+                    tmem_ld_wait();
+                    if (lane < 16)
+#pragma unroll
+                        for (uint32_t n = 0; n < 32; ++n) {
+                            const uint32_t col = t * 64 + half_id * 32 + n;
+                            if (col < sh.in_dim) atomicAdd(w_in + m * sh.in_dim + col, __uint_as_float(v[n]));
+                        }
+                }
         }
-        for (uint32_t l = 0; l < sh.n_hid; ++l)
-#pragma unroll
-            for (uint32_t half_id = 0; half_id < 2; ++half_id) {
-                uint32_t v[32];
-                tmem_ld32(d_whid + 64 * l + lane_sel + half_id * 32, v);
-                tmem_ld_wait();
-                if (lane < 16)
-#pragma unroll
-                    for (uint32_t n = 0; n < 32; ++n)
-                        atomicAdd(w_hid + (size_t)l * kHid * kHid + m * kHid + half_id * 32 + n, __uint_as_float(v[n]));
-            }
-        for (uint32_t t = 0; t < sh.kt_in; ++t)
-#pragma unroll
-            for (uint32_t half_id = 0; half_id < 2; ++half_id) {
-                uint32_t v[32];
-                tmem_ld32(d_win + 64 * t + lane_sel + half_id * 32, v);
-                tmem_ld_wait();
-                if (lane < 16)
-#pragma unroll
-                    for (uint32_t n = 0; n < 32; ++n) {
-                        const uint32_t col = t * 64 + half_id * 32 + n;
-                        if (col < sh.in_dim) atomicAdd(w_in + m * sh.in_dim + col, __uint_as_float(v[n]));
-                    }
-            }
     }
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 512);
+    if (warp == kWG * 4) tmem_dealloc(tmem, 512);
 }
 
 __global__ void k_f32_to_f16(const float *__restrict__ src, __half *__restrict__ dst, size_t n) {
@@ -448,7 +533,7 @@ int check_shape(uint32_t B, uint32_t in_dim, uint32_t out_dim, uint32_t hidden, 
     sh->kt_in = (in_dim + 63) / 64;
     sh->n_hid = nl - 1;
     sh->w_in_elems = kHid * in_dim;
-    if (128 + 64 * sh->n_hid + 64 * sh->kt_in > 512) return LNB_ERR_UNSUPPORTED;   // TMEM budget (backward)
+    if (192 + 64 * sh->n_hid + 64 * sh->kt_in > 512) return LNB_ERR_UNSUPPORTED;   // TMEM budget (backward)
     return LNB_OK;
 }
 
@@ -456,7 +541,10 @@ size_t fwd_smem(const Shape &sh) {
     return 1024 + (size_t)sh.kt_in * kWTileBytes + (size_t)sh.n_hid * kWTileBytes + 2048 +
            (size_t)sh.kt_in * kTileBytes + kTileBytes + 64;
 }
-size_t bwd_smem(const Shape &sh) { return fwd_smem(sh) + 2 * (size_t)kTileBytes; }
+size_t bwd_smem(const Shape &sh) {
+    return 1024 + (size_t)sh.kt_in * kWTileBytes + (size_t)sh.n_hid * kWTileBytes + 2048 +
+           (size_t)kWG * (2 + sh.n_hid + 1 + sh.kt_in) * kTileBytes + 64;
+}
 
 int sm_count() {
     static int n = 0;
@@ -522,6 +610,24 @@ size_t lnb_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_di
     return sizeof(float) * (size_t)hidden_dim * ((size_t)input_dim + (size_t)hidden_dim * (num_layers - 1) + output_dim);
 }
 
+static int ffmlp_backward_impl(const void *grad, const void *inputs, const void *weights, const void *forward_buffer,
+                               uint32_t B, const Shape &sh, int calc_grad_inputs, void *backward_buffer,
+                               void *grad_inputs, float *wgrad_f32, cudaStream_t st) {
+    const size_t smem = bwd_smem(sh);
+    cudaError_t e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    if (smem > 227 * 1024) return LNB_ERR_UNSUPPORTED;
+    const uint32_t cap = (uint32_t)sm_count();   // 512 TMEM columns: one CTA per SM, two row tiles in flight each
+    const uint32_t pairs = (B / kRows + kWG - 1) / kWG;
+    const uint32_t grid = pairs < cap ? pairs : cap;
+    k_ffmlp_bwd<<<grid, kBwdThreads, smem, st>>>(
+        static_cast<const __half *>(grad), static_cast<const __half *>(inputs), static_cast<const __half *>(weights),
+        static_cast<const __half *>(forward_buffer), B, sh, static_cast<__half *>(backward_buffer),
+        calc_grad_inputs ? static_cast<__half *>(grad_inputs) : nullptr, wgrad_f32);
+    count_launch();
+    return launch_status();
+}
+
 int lnb_ffmlp_backward(const void *grad, const void *inputs, const void *weights, const void *forward_buffer,
                        uint32_t B, uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
                        uint32_t num_layers, uint32_t activation, uint32_t output_activation,
@@ -539,17 +645,8 @@ int lnb_ffmlp_backward(const void *grad, const void *inputs, const void *weights
     cudaStream_t st = as_stream(stream);
     cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
     if (e != cudaSuccess) return (int)e;
-    const size_t smem = bwd_smem(sh);
-    e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    const uint32_t cap = (uint32_t)sm_count();   // 512 TMEM columns: one CTA per SM
-    const uint32_t grid = (B / kRows) < cap ? (B / kRows) : cap;
-    k_ffmlp_bwd<<<grid, kThreads, smem, st>>>(
-        static_cast<const __half *>(grad), static_cast<const __half *>(inputs), static_cast<const __half *>(weights),
-        static_cast<const __half *>(forward_buffer), B, sh, static_cast<__half *>(backward_buffer),
-        calc_grad_inputs ? static_cast<__half *>(grad_inputs) : nullptr, static_cast<float *>(workspace));
-    count_launch();
-    rc = launch_status();
+    rc = ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, backward_buffer,
+                             grad_inputs, static_cast<float *>(workspace), st);
     if (rc != LNB_OK) return rc;
     if (grad_weights) {
         const size_t n = need / sizeof(float);
@@ -559,6 +656,21 @@ int lnb_ffmlp_backward(const void *grad, const void *inputs, const void *weights
         rc = launch_status();
     }
     return rc;
+}
+
+int lnb_ffmlp_backward_accumulate(const void *grad, const void *inputs, const void *weights,
+                                  const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                  uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                  uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
+                                  float *grad_weights_f32, lnb_stream_t stream) {
+    if (!grad || !inputs || !weights || !forward_buffer || !grad_weights_f32) return LNB_ERR_INVALID_ARGUMENT;
+    if (calc_grad_inputs && !grad_inputs) return LNB_ERR_INVALID_ARGUMENT;
+    Shape sh;
+    int rc = check_shape(B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh);
+    if (rc != LNB_OK) return rc;
+    if (B == 0) return LNB_OK;
+    return ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, nullptr, grad_inputs,
+                               grad_weights_f32, as_stream(stream));
 }
 
 int lnb_allocate_splitk(size_t size) {

@@ -1,0 +1,403 @@
+"""Fused LiDAR-field training engine: one optimiser step of the reference's hot path
+(march -> hash-grid -> density MLP -> LiDAR head -> composite -> loss -> backward -> Adam) as ~17 launches of
+liblnb200.so kernels on one stream, captured in a CUDA graph, with no autograd, no host sync and no allocation
+inside the step.
+
+What it replaces in the reference (SURVEY.md sections 3.1-3.2): `Trainer.train_step` (nerf/utils.py:697-734) +
+`NeRFRenderer.run` (nerf/renderer.py:99-298) + `NeRFNetwork.density/color` (nerf/network.py:162-237) +
+`torch.optim.Adam`/GradScaler (main_lidarnerf.py:389-391, nerf/utils.py:1221-1223), in occupancy-march mode
+(the `run_cuda` glue the reference lacks).
+
+Parameters live in ONE flat fp32 vector [hash table | density-MLP weights | LiDAR-head weights] with a flat
+fp16 shadow the kernels read, so Adam and the data-parallel gradient exchange are single passes over one buffer.
+"""
+import math
+from dataclasses import dataclass
+
+import numpy as np
+import torch
+
+from ..backend import (_raymarching as rm, _ffmlp as ff, adam_step)
+from .._lib import lib, check, u32, f32, i32, vp
+from ..gridencoder import level_offsets
+
+
+@dataclass
+class FieldConfig:
+    # scene / march (main_lidarnerf.py defaults; configs/kitti360_1908.txt)
+    bound: float = 1.0
+    grid_size: int = 128                 # renderer.py:75
+    min_near_lidar: float = 0.010784853507573345   # = opt.scale (main_lidarnerf.py:286-287)
+    far_factor: float = 81.0             # renderer.py:134-138
+    dt_gamma: float = 0.0
+    max_steps: int = 1024
+    T_thresh: float = 1e-4
+    density_scale: float = 1.0
+    density_thresh: float = 10.0         # main_lidarnerf.py:210-215
+    # hash grid (configs/kitti360_1908.txt:7, main_lidarnerf.py:68-69)
+    num_levels: int = 16
+    level_dim: int = 2
+    base_resolution: int = 16
+    desired_resolution: int = 32768
+    log2_hashmap_size: int = 19
+    # MLPs (ffmlp 64x2 each; network.py:45-99 shapes)
+    hidden_dim: int = 64
+    sigma_layers: int = 2                # FFMLP num_layers
+    head_layers: int = 2
+    freq_degree: int = 12                # network.py:83
+    geo_feat_dim: int = 15
+    # loss (configs/kitti360_1908.txt:2-4)
+    alpha_d: float = 1e3
+    alpha_r: float = 1.0
+    alpha_i: float = 10.0
+    # optimiser (main_lidarnerf.py:389-391, lr default 1e-2)
+    lr: float = 1e-2
+    beta1: float = 0.9
+    beta2: float = 0.99
+    eps: float = 1e-15
+    loss_scale: float = 128.0            # static loss scale for the fp16 gradient chain (GradScaler's role)
+    grid_update_interval: int = 16
+    perturb: bool = True                 # jitter the march start (Trainer.train_step passes perturb=True)
+    seed: int = 0
+
+    @property
+    def cascade(self):
+        return 1 + math.ceil(math.log2(self.bound))   # renderer.py:74
+
+    @property
+    def head_in_dim(self):
+        raw = 3 + 6 * self.freq_degree + self.geo_feat_dim        # 75 + 15 = 90
+        return (raw + 15) // 16 * 16                               # padded to 96 for the tensor cores
+
+
+def _ck(status, what):
+    check(status, what)
+
+
+class LidarFieldEngine:
+    def __init__(self, cfg: FieldConfig, n_rays: int, device="cuda:0", sample_budget: int = None):
+        self.cfg = cfg
+        self.dev = torch.device(device)
+        self.N = int(n_rays)
+        c = cfg
+        dev = self.dev
+        gen = torch.Generator(device="cpu").manual_seed(c.seed)
+
+        # ---- parameters -------------------------------------------------------------------------------------
+        pls = float(np.exp2(np.log2(c.desired_resolution / c.base_resolution) / (c.num_levels - 1)))
+        self.per_level_scale = pls
+        self.S = float(np.log2(pls))
+        offs = level_offsets(3, c.num_levels, c.base_resolution, pls, c.log2_hashmap_size, False)
+        self.offsets = torch.from_numpy(offs).to(dev)
+        self.n_rows = int(offs[-1])
+        n_table = self.n_rows * c.level_dim
+        self.enc_dim = c.num_levels * c.level_dim
+        n_sigma = c.hidden_dim * (self.enc_dim + c.hidden_dim * (c.sigma_layers - 1) + 16)
+        n_head = c.hidden_dim * (c.head_in_dim + c.hidden_dim * (c.head_layers - 1) + 16)
+        self.n_table, self.n_sigma, self.n_head = n_table, n_sigma, n_head
+        n = n_table + n_sigma + n_head
+        self.n_params = n
+        P = torch.empty(n, dtype=torch.float32)
+        P[:n_table].uniform_(-1e-4, 1e-4, generator=gen)                                   # grid.py:202-204
+        bound_w = math.sqrt(3 / c.hidden_dim)                                              # ffmlp.py:242-245
+        P[n_table:].uniform_(-bound_w, bound_w, generator=gen)
+        self.P = P.to(dev)
+        self.G = torch.zeros(n, dtype=torch.float32, device=dev)
+        self.m = torch.zeros_like(self.G)
+        self.v = torch.zeros_like(self.G)
+        self.Ph = self.P.to(torch.float16)
+        self.table_h = self.Ph[:n_table].view(self.n_rows, c.level_dim)
+        self.w_sigma_h = self.Ph[n_table:n_table + n_sigma]
+        self.w_head_h = self.Ph[n_table + n_sigma:]
+        self.g_table = self.G[:n_table]
+        self.g_sigma_w = self.G[n_table:n_table + n_sigma]
+        self.g_head_w = self.G[n_table + n_sigma:]
+        self.step_count = 0
+
+        # ---- occupancy state -------------------------------------------------------
+        H3 = c.grid_size ** 3
+        self.density_grid = torch.zeros(c.cascade, H3, dtype=torch.float32, device=dev)
+        self.prior_grid = torch.zeros(c.cascade, H3, dtype=torch.float32, device=dev)    # LiDAR free-space prior
+        self.bitfield = torch.full((c.cascade * H3 // 8,), 255, dtype=torch.uint8, device=dev)
+        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.mean_density = 0.0
+
+        # ---- static per-ray buffers ------------------------------------------------------------------------
+        N = self.N
+        f = dict(dtype=torch.float32, device=dev)
+        self.rays_o = torch.zeros(N, 3, **f)
+        self.rays_d = torch.zeros(N, 3, **f)
+        self.gt = torch.zeros(N, 3, **f)
+        self.nears = torch.full((N,), c.min_near_lidar, **f)
+        self.fars = self.nears * c.far_factor
+        self.noises = torch.zeros(N, **f)
+        self.t0 = torch.zeros(N, **f)
+        self.rays = torch.zeros(N, 3, dtype=torch.int32, device=dev)
+        self.ws = torch.zeros(N, **f)
+        self.depth = torch.zeros(N, **f)
+        self.image = torch.zeros(N, 2, **f)
+        self.g_ws = torch.zeros(N, **f)
+        self.g_depth = torch.zeros(N, **f)
+        self.g_image = torch.zeros(N, 2, **f)
+        self.loss_acc = torch.zeros(1, **f)
+        two_sqrt3 = 2 * 1.7320508075688772
+        self.dt_min = np.float32(two_sqrt3) / np.float32(c.max_steps)
+        self.dt_max = np.float32(two_sqrt3) * np.float32(1 << (c.cascade - 1)) / np.float32(c.grid_size)
+
+        self.M = 0
+        self._graph = None
+        self._alloc_samples(sample_budget or N * 64)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _alloc_samples(self, M):
+        M = max(128, (int(M) + 127) // 128 * 128)
+        if M == self.M:
+            return
+        self.M = M
+        self._graph = None
+        dev, c = self.dev, self.cfg
+        f = dict(dtype=torch.float32, device=dev)
+        h = dict(dtype=torch.float16, device=dev)
+        self.xyzs = torch.zeros(M, 3, **f)
+        self.dirs = torch.zeros(M, 3, **f)
+        self.deltas = torch.zeros(M, 2, **f)
+        self.enc = torch.empty(M, self.enc_dim, **h)
+        self.sig_out = torch.empty(M, 16, **h)
+        self.fb_sigma = torch.empty(c.sigma_layers, M, c.hidden_dim, **h)
+        self.sigma = torch.empty(M, **f)
+        self.head_in = torch.empty(M, c.head_in_dim, **h)
+        self.head_out = torch.empty(M, 16, **h)
+        self.fb_head = torch.empty(c.head_layers, M, c.hidden_dim, **h)
+        self.rgb = torch.empty(M, 2, **f)
+        self.g_sigma = torch.zeros(M, **f)
+        self.g_rgb = torch.zeros(M, 2, **f)
+        self.g_head_out = torch.empty(M, 16, **h)
+        self.g_head_in = torch.empty(M, c.head_in_dim, **h)
+        self.g_sig_out = torch.empty(M, 16, **h)
+        self.g_enc = torch.empty(M, self.enc_dim, **h)
+
+    @staticmethod
+    def _s():
+        return vp(torch.cuda.current_stream().cuda_stream)
+
+    # ------------------------------------------------------------------------------------------------------
+    def _forward_backward(self):
+        """Everything between 'rays are in the static buffers' and 'flat gradient is complete'."""
+        c, N, M, s = self.cfg, self.N, self.M, self._s()
+        p = lambda t: vp(t.data_ptr())   # noqa: E731
+        self.counter.zero_()
+        if c.perturb:
+            self.noises.uniform_(0, 1)
+        else:
+            self.noises.zero_()
+        # march start per ray, for the absolute-depth term of the loss (raymarching.cu:375)
+        torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
+        torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
+
+        rm.march_rays_train(self.rays_o, self.rays_d, self.bitfield, c.bound, c.dt_gamma, c.max_steps, N, c.cascade,
+                            c.grid_size, M, self.nears, self.fars, self.xyzs, self.dirs, self.deltas, self.rays,
+                            self.counter, self.noises)
+        _ck(lib.lnb_zero_sample_tail(p(self.xyzs), p(self.dirs), p(self.deltas), p(self.counter), u32(M), s), "zero_tail")
+        _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
+                                           u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
+                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), s), "grid_fwd")
+        ff.ffmlp_forward(self.enc, self.w_sigma_h, M, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6,
+                         self.fb_sigma, self.sig_out)
+        _ck(lib.lnb_field_head_input(p(self.sig_out), p(self.dirs), u32(M), u32(c.freq_degree), u32(c.head_in_dim),
+                                     f32(c.density_scale), p(self.sigma), p(self.head_in), s), "head_input")
+        ff.ffmlp_forward(self.head_in, self.w_head_h, M, c.head_in_dim, 16, c.hidden_dim, c.head_layers, 0, 6,
+                         self.fb_head, self.head_out)
+        _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), s), "head_rgb")
+        rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2, self.ws,
+                                           self.depth, self.image)
+        _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N), f32(c.alpha_d),
+                               f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale), p(self.g_ws), p(self.g_depth),
+                               p(self.g_image), p(self.loss_acc), s), "lidar_loss")
+        # ---- backward ----
+        self.g_sigma.zero_()
+        self.g_rgb.zero_()
+        rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb, self.deltas,
+                                            self.rays, self.ws, self.depth, self.image, M, N, c.T_thresh, 2,
+                                            self.g_sigma, self.g_rgb)
+        _ck(lib.lnb_field_head_out_grad(p(self.g_rgb), p(self.rgb), u32(M), p(self.g_head_out), s), "head_out_grad")
+        _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_head_out), p(self.head_in), p(self.w_head_h), p(self.fb_head),
+                                              u32(M), u32(c.head_in_dim), u32(16), u32(c.hidden_dim),
+                                              u32(c.head_layers), u32(0), u32(6), i32(1), p(self.g_head_in),
+                                              p(self.g_head_w), s), "ffmlp_bwd(head)")
+        _ck(lib.lnb_field_sigma_out_grad(p(self.g_sigma), p(self.sig_out), p(self.g_head_in), u32(M),
+                                         u32(c.head_in_dim), u32(c.freq_degree), f32(c.density_scale),
+                                         p(self.g_sig_out), s), "sigma_out_grad")
+        _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h), p(self.fb_sigma),
+                                              u32(M), u32(self.enc_dim), u32(16), u32(c.hidden_dim),
+                                              u32(c.sigma_layers), u32(0), u32(6), i32(1), p(self.g_enc),
+                                              p(self.g_sigma_w), s), "ffmlp_bwd(sigma)")
+        _ck(lib.lnb_grid_encode_backward_ex(p(self.g_enc), p(self.xyzs), p(self.table_h), p(self.offsets),
+                                            p(self.g_table), u32(M), u32(3), u32(c.level_dim), u32(c.num_levels),
+                                            f32(self.S), u32(c.base_resolution), vp(0), vp(0), u32(0), i32(0), u32(0),
+                                            i32(1), i32(1), f32(c.bound), i32(1), s), "grid_bwd")
+
+    def _optimizer(self, lr=None):
+        c = self.cfg
+        self.step_count += 1
+        adam_step(self.P, self.G, self.m, self.v, self.Ph, c.lr if lr is None else lr, c.beta1, c.beta2, c.eps,
+                  self.step_count, grad_scale=1.0 / (c.loss_scale * self._world()), zero_grad=True)
+
+    @staticmethod
+    def _world():
+        import torch.distributed as dist
+        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+    def _allreduce(self):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.all_reduce(self.G)   # SUM; the 1/world factor is folded into Adam's grad_scale
+
+    # ------------------------------------------------------------------------------------------------------
+    def set_batch(self, rays_o, rays_d, gt):
+        """Device tensors [N,3] each (gt = ray-drop, intensity, depth) -> static buffers."""
+        self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
+        self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=True)
+        self.gt.copy_(gt.reshape(-1, 3), non_blocking=True)
+
+    def train_step(self, use_graph=True):
+        """One optimiser step on the batch currently in the static buffers."""
+        if use_graph:
+            if self._graph is None:
+                self._capture()
+            self._graph.replay()          # march ... grid backward: one graph launch
+        else:
+            self._forward_backward()
+        self._allreduce()                 # data parallel: one NCCL all-reduce of the flat gradient (no-op for 1 GPU)
+        self._optimizer()                 # bias corrections change every step -> Adam stays outside the graph
+        if self.cfg.grid_update_interval > 0 and self.step_count % self.cfg.grid_update_interval == 0:
+            self.update_density_grid()
+
+    def _capture(self):
+        # warm up on a side stream (module loads, cudaFuncSetAttribute) before capturing
+        side = torch.cuda.Stream(device=self.dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            g_backup = self.G.clone()
+            self._forward_backward()
+            self.G.copy_(g_backup)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._forward_backward()
+        self.G.zero_()   # capture does not execute, but keep the gradient clean regardless
+        self._graph = g
+
+    # ------------------------------------------------------------------------------------------------------
+    def samples_last_step(self):
+        """(samples produced, rays marched) of the last step - one D2H sync; not called inside the timed loop."""
+        cnt = self.counter.cpu()
+        return int(cnt[0]), int(cnt[1])
+
+    def fit_sample_budget(self, headroom=1.15):
+        """Size M from the count of the last step (the reference's mean_count logic, raymarching.py:228-233)."""
+        produced, _ = self.samples_last_step()
+        want = max(128, int(produced * headroom))
+        if want > self.M or want < 0.7 * self.M:
+            self._alloc_samples(want)
+        return self.M
+
+    def read_loss(self, reset=True):
+        v = float(self.loss_acc.item())
+        if reset:
+            self.loss_acc.zero_()
+        return v
+
+    # ---- occupancy grid --------------------------------------------------------------------------------------
+    def cell_centers(self, cas, jitter=True):
+        """World-space centres (optionally jittered inside the cell) of all H^3 cells of one cascade, in Morton
+        order (the layout packbits / the march expect)."""
+        c = self.cfg
+        H = c.grid_size
+        idx = torch.arange(H ** 3, dtype=torch.int32, device=self.dev)
+        from ..raymarching import morton3D_invert
+        coords = morton3D_invert(idx).float()                        # [H^3, 3] integer cell coordinates
+        xyz = 2 * coords / (H - 1) - 1                               # [-1, 1] (upstream convention)
+        bound = min(2.0 ** cas, c.bound)
+        half = bound / H
+        xyz = xyz * (bound - half)
+        if jitter:
+            xyz = xyz + (torch.rand_like(xyz) * 2 - 1) * half
+        return xyz
+
+    @torch.no_grad()
+    def query_density(self, xyz):
+        """sigma at arbitrary points [B,3] (inference kernels; B padded to 128)."""
+        c = self.cfg
+        B = xyz.shape[0]
+        Bp = (B + 127) // 128 * 128
+        pts = torch.zeros(Bp, 3, dtype=torch.float32, device=self.dev)
+        pts[:B] = xyz
+        enc = torch.empty(Bp, self.enc_dim, dtype=torch.float16, device=self.dev)
+        s = self._s()
+        p = lambda t: vp(t.data_ptr())   # noqa: E731
+        _ck(lib.lnb_grid_encode_forward_ex(p(pts), p(self.table_h), p(self.offsets), p(enc), u32(Bp), u32(3),
+                                           u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
+                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), s), "grid_fwd")
+        out = torch.empty(Bp, 16, dtype=torch.float16, device=self.dev)
+        ff.ffmlp_inference(enc, self.w_sigma_h, Bp, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6, None, out)
+        return torch.exp(out[:B, 0].float()) * c.density_scale
+
+    @torch.no_grad()
+    def update_density_grid(self, decay=0.95, full=None):
+        """EMA-max refresh of the density grid from the current network + packbits, merged
+        with the LiDAR prior grid (cells a GT return falls into stay occupied)."""
+        from ..raymarching import packbits
+        c = self.cfg
+        H3 = c.grid_size ** 3
+        n_updates = self.step_count // max(c.grid_update_interval, 1)
+        full = (n_updates <= 16) if full is None else full
+        for cas in range(c.cascade):
+            xyz = self.cell_centers(cas)
+            if full:
+                sel = None
+                sig = self.query_density(xyz)
+            else:   # H^3/4 uniform random cells + H^3/4 currently occupied cells
+                nq = H3 // 4
+                rnd = torch.randint(0, H3, (nq,), device=self.dev)
+                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                if occ.numel() > 0:
+                    occ = occ[torch.randint(0, occ.numel(), (nq,), device=self.dev)]
+                    sel = torch.cat([rnd, occ])
+                else:
+                    sel = rnd
+                sig = self.query_density(xyz[sel])
+            if sel is None:
+                self.density_grid[cas] = torch.maximum(self.density_grid[cas] * decay, sig)
+            else:
+                cur = self.density_grid[cas]
+                cur[sel] = torch.maximum(cur[sel] * decay, sig)
+        merged = torch.maximum(self.density_grid, self.prior_grid)
+        self.mean_density = float(merged.clamp(min=0).mean().item())
+        thresh = min(self.mean_density, c.density_thresh)
+        packbits(merged, thresh, self.bitfield)
+
+    @torch.no_grad()
+    def seed_occupancy_from_points(self, points, dilate=1, value=1e4):
+        """LiDAR prior: mark the cells containing GT returns (and their `dilate`-neighbourhood) as occupied in every
+        cascade that contains them.  points: [P,3] world coordinates (already scaled into [-bound, bound])."""
+        from ..raymarching import morton3D, packbits
+        c = self.cfg
+        H = c.grid_size
+        self.prior_grid.zero_()
+        offs = torch.stack(torch.meshgrid(*([torch.arange(-dilate, dilate + 1, device=self.dev)] * 3), indexing="ij"),
+                           -1).reshape(-1, 3)
+        for cas in range(c.cascade):
+            bound = min(2.0 ** cas, c.bound)
+            inside = (points.abs() <= bound).all(-1)
+            pts = points[inside]
+            if pts.numel() == 0:
+                continue
+            cell = torch.clamp((0.5 * (pts / bound + 1) * H).long(), 0, H - 1)
+            cell = (cell[:, None, :] + offs[None]).reshape(-1, 3).clamp(0, H - 1)
+            cell = torch.unique(cell, dim=0)
+            idx = morton3D(cell.int()).long()
+            self.prior_grid[cas, idx] = value
+        merged = torch.maximum(self.density_grid, self.prior_grid)
+        self.mean_density = float(merged.clamp(min=0).mean().item())
+        packbits(merged, min(self.mean_density, c.density_thresh), self.bitfield)

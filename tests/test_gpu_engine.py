@@ -1,0 +1,186 @@
+"""GPU tests of the fused training engine and of the B2 (reference-shaped) Python wrappers."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def test_fused_step_matches_cpu_restatement():
+    from oracle import check_engine
+    eng, gpu, cpu = check_engine.run_pair(n_rays=256, device=DEV)
+    assert gpu["n_samples"] > 1000, "the test scene must produce samples"
+    check_engine.compare(gpu, cpu, eng.n_table)
+
+
+def test_fused_step_full_size_table_matches_cpu_restatement():
+    from oracle import check_engine
+    cfg = check_engine.small_config(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
+    eng, gpu, cpu = check_engine.run_pair(n_rays=128, device=DEV, cfg=cfg, seed=1)
+    check_engine.compare(gpu, cpu, eng.n_table)
+
+
+def test_graph_replay_equals_eager():
+    from oracle import check_engine
+    from lidar_nerf_b200.nerf.engine import LidarFieldEngine
+    cfg = check_engine.small_config(perturb=False)
+    eng, gpu, _ = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg)
+    g_eager = eng.G.clone()
+    eng.G.zero_()
+    eng._capture()
+    eng.G.zero_()
+    eng.loss_acc.zero_()
+    eng._graph.replay()
+    torch.cuda.synchronize()
+    rel = float((eng.G - g_eager).norm() / g_eager.norm())
+    assert rel < 1e-4, rel
+    np.testing.assert_allclose(float(eng.loss_acc.item()), gpu["loss"], rtol=1e-5)
+
+
+def test_training_reduces_the_loss_on_the_synthetic_sequence():
+    from lidar_nerf_b200.nerf.engine import LidarFieldEngine, FieldConfig
+    from lidar_nerf_b200.data.synthetic import SyntheticLidarSequence
+    seq = SyntheticLidarSequence(H=16, W=256, n_frames=2, device=DEV)
+    cfg = FieldConfig(log2_hashmap_size=15, desired_resolution=2048, grid_update_interval=0, lr=5e-3)
+    eng = LidarFieldEngine(cfg, 1024, device=DEV, sample_budget=1024 * 96)
+    eng.seed_occupancy_from_points(seq.surface_points())
+    gen = torch.Generator().manual_seed(0)
+    losses = []
+    for it in range(150):
+        ro, rd, gt = seq.sample_batch(1024, generator=gen, device=DEV)
+        eng.set_batch(ro, rd, gt)
+        eng.train_step(use_graph=(it >= 3))
+        if it == 2:
+            eng.fit_sample_budget(1.3)
+        if it % 10 == 9:
+            losses.append(eng.read_loss() / 10)
+        if it == 0:
+            eng.read_loss()
+    assert np.isfinite(losses).all(), losses
+    assert losses[-1] < 0.6 * losses[0], losses
+    assert torch.isfinite(eng.P).all()
+
+
+def test_density_grid_refresh_and_prior():
+    from lidar_nerf_b200.nerf.engine import LidarFieldEngine, FieldConfig
+    cfg = FieldConfig(log2_hashmap_size=14, desired_resolution=512, grid_update_interval=0)
+    eng = LidarFieldEngine(cfg, 128, device=DEV)
+    pts = torch.tensor([[0.1, 0.2, -0.3], [-0.5, 0.5, 0.0]], device=DEV)
+    eng.seed_occupancy_from_points(pts, dilate=0)
+    bits = np.unpackbits(eng.bitfield.cpu().numpy(), bitorder="little")
+    assert bits.sum() == 2
+    from oracle import oracle as orc
+    cell = np.clip((0.5 * (pts.cpu().numpy() + 1) * 128).astype(np.int32), 0, 127)
+    assert bits[orc.morton3D(cell).astype(np.int64)].all()
+    eng.step_count = 16
+    eng.update_density_grid(full=True)
+    bits2 = np.unpackbits(eng.bitfield.cpu().numpy(), bitorder="little")
+    assert bits2[orc.morton3D(cell).astype(np.int64)].all(), "prior cells must stay occupied"
+    assert eng.density_grid.max() > 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B2 wrappers: same call signatures as the reference's modules, autograd included
+# ---------------------------------------------------------------------------------------------------------------
+def test_b2_grid_encoder_module_forward_backward(orc):
+    from lidar_nerf_b200.gridencoder import GridEncoder
+    torch.manual_seed(0)
+    enc = GridEncoder(input_dim=3, num_levels=8, level_dim=2, base_resolution=16, log2_hashmap_size=15,
+                      desired_resolution=512).to(DEV)
+    enc.embeddings.data.uniform_(-1, 1)
+    x = (torch.rand(500, 3, device=DEV) * 2 - 1)
+    y = enc(x, bound=1)
+    assert y.shape == (500, 16) and y.dtype == torch.float32
+    x01 = ((x + 1) / 2).cpu().numpy()
+    ls = (torch.exp2(torch.arange(8, device=DEV, dtype=torch.float32) * torch.tensor(float(np.log2(enc.per_level_scale)), device=DEV)) * 16.0 - 1.0).cpu().numpy()
+    want = orc.grid_encode_forward(x01, enc.embeddings.detach().cpu().numpy(), enc.offsets.cpu().numpy(),
+                                   enc.per_level_scale, 16, level_scales=ls)
+    np.testing.assert_allclose(y.detach().cpu().numpy(), want, rtol=1e-4, atol=1e-5)
+    g = torch.randn_like(y)
+    (y * g).sum().backward()
+    gt = orc.grid_encode_backward(g.cpu().numpy(), x01, tuple(enc.embeddings.shape), enc.offsets.cpu().numpy(),
+                                  enc.per_level_scale, 16, level_scales=ls)
+    np.testing.assert_allclose(enc.embeddings.grad.cpu().numpy(), gt, rtol=1e-4, atol=1e-5)
+    # autocast: half table for even C (grid.py:54-57)
+    with torch.autocast("cuda", dtype=torch.float16):
+        yh = enc(x, bound=1)
+    assert yh.dtype == torch.float16
+    np.testing.assert_allclose(yh.float().detach().cpu().numpy(), want, rtol=1e-2, atol=1e-2)
+
+
+def test_b2_freq_sh_modules(orc):
+    from lidar_nerf_b200.freqencoder import FreqEncoder
+    from lidar_nerf_b200.shencoder import SHEncoder
+    x = (torch.rand(300, 3, device=DEV) * 2 - 1).requires_grad_(True)
+    fe = FreqEncoder(3, 6)
+    y = fe(x)
+    assert y.shape == (300, 39)
+    g = torch.randn_like(y)
+    (y * g).sum().backward()
+    want = orc.freq_encode_backward(g.cpu().numpy(), y.detach().cpu().numpy(), 3, 6)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), want, rtol=1e-4, atol=1e-4)
+    x2 = (torch.rand(300, 3, device=DEV) * 2 - 1).requires_grad_(True)
+    sh = SHEncoder(3, 4)
+    y2 = sh(x2)
+    g2 = torch.randn_like(y2)
+    (y2 * g2).sum().backward()
+    out, dy = orc.sh_encode_forward(x2.detach().cpu().numpy(), 4, True)
+    np.testing.assert_allclose(y2.detach().cpu().numpy(), out, rtol=1e-4, atol=2e-5)
+    np.testing.assert_allclose(x2.grad.cpu().numpy(), orc.sh_encode_backward(g2.cpu().numpy(), 4, dy), rtol=1e-3, atol=1e-4)
+
+
+def test_b2_ffmlp_module(orc):
+    from lidar_nerf_b200.ffmlp import FFMLP
+    mlp = FFMLP(32, 3, 64, 2).to(DEV)
+    assert mlp.weights.numel() == 64 * (32 + 64 + 16)
+    x = (torch.rand(200, 32, device=DEV) - 0.5).requires_grad_(True)    # B not a multiple of 128 -> padded inside
+    mlp.train()
+    with torch.autocast("cuda", dtype=torch.float16):
+        y = mlp(x)
+    assert y.shape == (200, 3) and y.dtype == torch.float16
+    want, fb = orc.ffmlp_forward(x.detach().cpu().numpy(), mlp.weights.detach().cpu().numpy(), 32, 16, 64, 2)
+    np.testing.assert_allclose(y.float().detach().cpu().numpy(), want[:, :3], rtol=3e-3, atol=3e-3)
+    g = torch.randn_like(y) * 0.1
+    (y * g).sum().backward()
+    gfull = np.zeros((200, 16), np.float32)
+    gfull[:, :3] = g.float().cpu().numpy()
+    gi, gw, _ = orc.ffmlp_backward(gfull, x.detach().cpu().numpy(), mlp.weights.detach().cpu().numpy(), fb, 32, 16, 64, 2)
+    np.testing.assert_allclose(x.grad.cpu().numpy(), gi, rtol=1e-2, atol=3e-3)
+    np.testing.assert_allclose(mlp.weights.grad.cpu().numpy(), gw, rtol=1e-2, atol=5e-3 * max(1.0, np.abs(gw).max()))
+    mlp.eval()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.float16):
+        y_inf = mlp(x.detach())
+    np.testing.assert_allclose(y_inf.float().cpu().numpy(), y.float().detach().cpu().numpy(), rtol=1e-3, atol=1e-3)
+
+
+def test_b2_raymarching_wrappers_roundtrip(orc):
+    import cases
+    from lidar_nerf_b200 import raymarching as rmw
+    c = cases.march_case(61, 300, 1, 1.0, 128, 0.3, False)
+    ro, rd = torch.from_numpy(c["rays_o"]).to(DEV), torch.from_numpy(c["rays_d"]).to(DEV)
+    aabb = torch.tensor([-1, -1, -1, 1, 1, 1.0], device=DEV)
+    nears, fars = rmw.near_far_from_aabb(ro, rd, aabb, 0.05)
+    bf = torch.from_numpy(c["bitfield"]).to(DEV)
+    counter = torch.zeros(2, dtype=torch.int32, device=DEV)
+    xyzs, dirs, deltas, rays = rmw.march_rays_train(ro, rd, 1.0, bf, 1, 128, nears, fars, counter, -1, False, 128, False,
+                                                    0, 512)
+    assert xyzs.shape[0] % 128 == 0 and int(counter[1]) == 300
+    sig = torch.rand(xyzs.shape[0], device=DEV, requires_grad=True)
+    rgb = torch.rand(xyzs.shape[0], 3, device=DEV, requires_grad=True)
+    ws, depth, img = rmw.composite_rays_train(sig * 30, rgb, deltas, rays)
+    (ws.sum() + img.sum()).backward()
+    assert torch.isfinite(sig.grad).all() and sig.grad.abs().sum() > 0
+    o_ws, o_d, o_img = orc.composite_rays_train_forward((sig * 30).detach().cpu().numpy(), rgb.detach().cpu().numpy(),
+                                                        deltas.cpu().numpy(), rays.cpu().numpy(), 1e-4)
+    np.testing.assert_allclose(ws.detach().cpu().numpy(), o_ws, rtol=1e-4, atol=1e-5)
+    # second call with a mean_count budget: no host sync path, fixed-size outputs
+    counter.zero_()
+    x2, d2, dl2, r2 = rmw.march_rays_train(ro, rd, 1.0, bf, 1, 128, nears, fars, counter, int(xyzs.shape[0]), False, 128,
+                                           False, 0, 512)
+    assert x2.shape[0] == xyzs.shape[0] + 128 - xyzs.shape[0] % 128 or x2.shape[0] >= xyzs.shape[0]
+    grid = torch.rand(1, 128 ** 3, device=DEV)
+    bits = rmw.packbits(grid, 0.5)
+    assert bits.shape[0] == 128 ** 3 // 8
+    idx = rmw.morton3D(torch.tensor([[1, 2, 3]], device=DEV))
+    assert rmw.morton3D_invert(idx).tolist() == [[1, 2, 3]]
