@@ -144,17 +144,20 @@ int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *
  *  - `in_bound` > 0: inputs are world coordinates in [-bound, bound], mapped to [0,1] inside the kernel exactly
  *    as GridEncoder.forward does, (x + bound) / (2 bound) (grid.py:213); 0 = inputs already in [0,1];
  *  - `accumulate_f32` != 0 (backward, dtype == LNB_F16): the incoming gradient is fp16 but grad_embeddings is an
- *    fp32 table accumulated with fp32 atomics (no fp16 rounding of small updates); dy_dx must be NULL. */
+ *    fp32 table accumulated with fp32 atomics (no fp16 rounding of small updates); dy_dx must be NULL;
+ *  - `n_active` (device pointer, nullable; [B, L*C] layout only): only the first round_up(*n_active, 128) rows are
+ *    processed - the sample counter written by lnb_march_rays_train, read on the device (no host sync). */
 int lnb_grid_encode_forward_ex(const float *inputs, const void *embeddings, const int32_t *offsets,
                                void *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                                uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners,
-                               uint32_t interp, int dtype, int layout, float in_bound, lnb_stream_t stream);
+                               uint32_t interp, int dtype, int layout, float in_bound,
+                               const int32_t *n_active, lnb_stream_t stream);
 int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const void *embeddings,
                                 const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D,
                                 uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx,
                                 void *grad_inputs, uint32_t gridtype, int align_corners,
                                 uint32_t interp, int dtype, int layout, float in_bound,
-                                int accumulate_f32, lnb_stream_t stream);
+                                int accumulate_f32, const int32_t *n_active, lnb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * freqencoder  (replaces lidarnerf/freqencoder/src/freqencoder.h, bindings.cpp:5-9)   fp32
@@ -209,7 +212,12 @@ int lnb_ffmlp_backward_accumulate(const void *grad, const void *inputs, const vo
                                   const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
                                   uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
                                   uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
-                                  float *grad_weights_f32, lnb_stream_t stream);
+                                  float *grad_weights_f32, const int32_t *n_active, lnb_stream_t stream);
+/* forward with the device-side row count (see lnb_grid_encode_forward_ex); forward_buffer == NULL = inference */
+int lnb_ffmlp_forward_ex(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                         uint32_t output_activation, void *forward_buffer, void *outputs, const int32_t *n_active,
+                         lnb_stream_t stream);
 /* ffmlp.cu:1030-1049 create/destroy split-K side streams.  This implementation accumulates the
  * weight gradient in tensor memory inside the backward kernel and needs no side streams; the
  * two symbols are kept so the reference's FFMLP.__init__ (ffmlp.py:230) binds unchanged. */
@@ -234,15 +242,19 @@ int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq,
  * (nerf/network.py:162-237, nerf/utils.py:707-734, dataset/base_dataset.py:85-100), one pass each.
  * ---------------------------------------------------------------------------------------- */
 
-/* zero xyzs/dirs/deltas rows [counter[0], M) on the device (what raymarching.py:235-237 does with full memsets) */
+/* The per-sample kernels below take `n_active` (nullable device pointer to the march's sample counter): rows at or
+ * beyond round_up(*n_active, 128) are skipped.
+ * zero xyzs/dirs/deltas rows [counter[0], round_up(counter[0], 128)) on the device: the padding inside the last
+ * partially filled tile (raymarching.py:235-237 zero-fills whole buffers on the host side every call) */
 int lnb_zero_sample_tail(float *xyzs, float *dirs, float *deltas, const int32_t *counter, uint32_t M,
                          lnb_stream_t stream);
 /* sigma_out [M,16] fp16 (density head output), dirs [M,3] ->
  *   sigma [M] fp32 = exp(h0) * density_scale ; head_in [M,in_pad] fp16 = [freq_enc(dir,degree) | geo_feat(15) | 0] */
 int lnb_field_head_input(const void *sigma_out, const float *dirs, uint32_t M, uint32_t degree, uint32_t in_pad,
-                         float density_scale, float *sigma, void *head_in, lnb_stream_t stream);
+                         float density_scale, float *sigma, void *head_in, const int32_t *n_active,
+                         lnb_stream_t stream);
 /* head_out [M,16] fp16 -> rgb [M,2] fp32 = sigmoid(h[0:2])  (ray-drop, intensity) */
-int lnb_field_head_rgb(const void *head_out, uint32_t M, float *rgb, lnb_stream_t stream);
+int lnb_field_head_rgb(const void *head_out, uint32_t M, float *rgb, const int32_t *n_active, lnb_stream_t stream);
 /* LiDAR loss (nerf/utils.py:726-734, mean over rays) and its gradient w.r.t. (weights_sum, depth, image[N,2]);
  * gt [N,3] = (ray-drop, intensity, depth); t0 [N] (nullable) = march start added as t0*weights_sum to depth;
  * loss_out[0] += loss; gradients are multiplied by loss_scale. */
@@ -250,10 +262,10 @@ int lnb_lidar_loss(const float *weights_sum, const float *depth, const float *im
                    const float *t0, uint32_t N, float alpha_d, float alpha_r, float alpha_i, float loss_scale,
                    float *g_weights_sum, float *g_depth, float *g_image, float *loss_out, lnb_stream_t stream);
 int lnb_field_head_out_grad(const float *g_rgb, const float *rgb, uint32_t M, void *g_head_out,
-                            lnb_stream_t stream);
+                            const int32_t *n_active, lnb_stream_t stream);
 int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const void *g_head_in, uint32_t M,
                              uint32_t in_pad, uint32_t degree, float density_scale, void *g_sigma_out,
-                             lnb_stream_t stream);
+                             const int32_t *n_active, lnb_stream_t stream);
 /* get_lidar_rays (dataset/base_dataset.py:85-100): pose [3x4 or 4x4 row-major], inds [N] flat pixel ids */
 int lnb_lidar_rays(const float *pose, const int32_t *inds, uint32_t N, uint32_t H, uint32_t W, float fov_up,
                    float fov, float *rays_o, float *rays_d, lnb_stream_t stream);

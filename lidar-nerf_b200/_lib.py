@@ -37,7 +37,7 @@ SYMBOLS = [
     "lnb_sh_encode_forward", "lnb_sh_encode_backward",
     "lnb_ffmlp_forward", "lnb_ffmlp_inference", "lnb_ffmlp_backward_workspace_bytes", "lnb_ffmlp_backward",
     "lnb_allocate_splitk", "lnb_free_splitk", "lnb_adam_step",
-    "lnb_grid_encode_forward_ex", "lnb_grid_encode_backward_ex", "lnb_ffmlp_backward_accumulate",
+    "lnb_grid_encode_forward_ex", "lnb_grid_encode_backward_ex", "lnb_ffmlp_backward_accumulate", "lnb_ffmlp_forward_ex",
     "lnb_zero_sample_tail", "lnb_field_head_input", "lnb_field_head_rgb", "lnb_lidar_loss",
     "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays",
 ]

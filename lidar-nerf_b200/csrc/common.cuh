@@ -35,6 +35,16 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// Number of rows a sample-parallel kernel has to process: all B of them, or - when the caller passes the device
+// counter the march kernel filled - the produced samples rounded up to a 128-row tile.  Lets the training step
+// size its buffers generously (no dropped rays) while the work tracks the real sample count without a host sync.
+__device__ __forceinline__ uint32_t active_rows(uint32_t B, const int32_t *__restrict__ n_active) {
+    if (!n_active) return B;
+    const int32_t n = *n_active;
+    const uint32_t up = ((uint32_t)(n > 0 ? n : 0) + 127u) & ~127u;
+    return up < B ? up : B;
+}
+
 template <typename T>
 __device__ __forceinline__ T warp_sum(T v) {
 #pragma unroll

@@ -107,7 +107,7 @@ __device__ __forceinline__ void issue_wgrad(uint32_t d, uint32_t a_tile, uint32_
 template <bool kSaveActs>
 __global__ void __launch_bounds__(kThreads)
 k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t B, Shape sh,
-            __half *__restrict__ fbuf, __half *__restrict__ Y) {
+            __half *__restrict__ fbuf, __half *__restrict__ Y, const int32_t *__restrict__ n_active) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_win = sbase;
@@ -142,7 +142,7 @@ k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t
     const uint32_t lane_sel = (warp * 32u) << 16;
 
     uint32_t phase = 0;
-    const uint32_t n_tiles = B / kRows;
+    const uint32_t n_tiles = active_rows(B, n_active) / kRows;   // B (the buffer stride) stays the full batch
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * kRows;
         // input tile -> smem
@@ -272,14 +272,15 @@ __device__ __forceinline__ void wg_store_tile_rows(uint32_t tid, uint32_t tile, 
 __global__ void __launch_bounds__(kBwdThreads, 1)
 k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __half *__restrict__ W,
             const __half *__restrict__ fbuf, uint32_t B, Shape sh, __half *__restrict__ bbuf,
-            __half *__restrict__ dX, float *__restrict__ wgrad /* fp32, flat weight layout */) {
+            __half *__restrict__ dX, float *__restrict__ wgrad /* fp32, flat weight layout */,
+            const int32_t *__restrict__ n_active) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t n_act = sh.n_hid + 1;                                  // saved activation tiles per row tile
     const uint32_t s_win = sbase;
     const uint32_t s_whid = s_win + sh.kt_in * kWTileBytes;
     const uint32_t s_wout = s_whid + sh.n_hid * kWTileBytes;
-    const uint32_t wg_bytes = (2 + n_act + sh.kt_in) * kTileBytes;        // G, dH, activations, X
+    const uint32_t wg_bytes = (1 + n_act + sh.kt_in) * kTileBytes;        // G (aliased by dH), activations, X
     const uint32_t s_wg0 = s_wout + 2048;
     const uint32_t s_bar = s_wg0 + kWG * wg_bytes;                        // ready[2], done[2], fin, slot
 
@@ -324,7 +325,7 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
     const uint32_t d_whid = tmem + 192;
     const uint32_t d_win = d_whid + 64 * sh.n_hid;
 
-    const uint32_t n_tiles = B / kRows;
+    const uint32_t n_tiles = active_rows(B, n_active) / kRows;
     const uint32_t stride_tiles = gridDim.x * kWG;
     const uint32_t n_iter = (n_tiles + stride_tiles - 1) / stride_tiles;
     const bool want_dx = dX != nullptr;
@@ -341,13 +342,13 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
                         const uint32_t tile = (it * gridDim.x + blockIdx.x) * kWG + g;
                         if (tile >= n_tiles) continue;
                         const uint32_t base = s_wg0 + g * wg_bytes;
-                        const uint32_t s_g = base, s_d = base + kTileBytes, s_h = base + 2 * kTileBytes;
+                        const uint32_t s_g = base, s_d = base, s_h = base + kTileBytes;   // dH overwrites G
                         const uint32_t s_x = s_h + n_act * kTileBytes;
                         const uint32_t d_acc = tmem + 64 * g;
                         mbar_wait(bar_ready0 + 8 * g, par_ready[g]);
                         par_ready[g] ^= 1;
                         fence_after_sync();
-                        // group 0 always owns a tile in iteration 0 and is served first: it initialises the accumulators
+                        // group 0 of a CTA that owns any tile is served first in iteration 0: it initialises the accumulators
                         const bool accw = !(it == 0 && g == 0);
                         if (ph == 0) {
                             issue_dgrad(d_acc, s_g, s_wout, 1);
@@ -372,7 +373,7 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
     } else {
         // ================= compute warpgroups =================
         const uint32_t base = s_wg0 + wg * wg_bytes;
-        const uint32_t s_g = base, s_d = base + kTileBytes, s_h = base + 2 * kTileBytes;
+        const uint32_t s_g = base, s_d = base, s_h = base + kTileBytes;   // dH overwrites G after phase 0
         const uint32_t s_x = s_h + n_act * kTileBytes;
         const uint32_t d_acc = tmem + 64 * wg;
         const uint32_t bar_ready = bar_ready0 + 8 * wg, bar_done = bar_done0 + 8 * wg;
@@ -384,9 +385,12 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
             if (tile >= n_tiles) break;
             const size_t row0 = (size_t)tile * kRows;
             // ---- all inputs of this tile at once ----
-            for (uint32_t q = tid; q < kRows * 2; q += 128) {
-                const uint32_t r = q >> 1, c = q & 1;
-                sts128(tile_chunk_addr(s_g, r, c), __ldg(reinterpret_cast<const uint4 *>(G + (row0 + r) * kOut + c * 8)));
+            // G: 16 valid columns (chunks 0,1); chunks 2..7 re-zeroed every tile because dH aliases this tile
+            for (uint32_t q = tid; q < kRows * 8; q += 128) {
+                const uint32_t r = q >> 3, c = q & 7;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                if (c < 2) v = __ldg(reinterpret_cast<const uint4 *>(G + (row0 + r) * kOut + c * 8));
+                sts128(tile_chunk_addr(s_g, r, c), v);
             }
             for (uint32_t l = 0; l < n_act; ++l)
                 wg_load_tiles(tid, s_h + l * kTileBytes, fbuf + ((size_t)l * B + row0) * kHid, kHid, kHid);
@@ -473,7 +477,7 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
     if (wg == 0) {
         mbar_wait(bar_fin, 0);
         fence_after_sync();
-        if (blockIdx.x * kWG < n_tiles) {
+        if (blockIdx.x * kWG < n_tiles) {   // this CTA accumulated something
             const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
             const uint32_t m = (warp & 3u) * 16 + lane;  // valid when lane < 16
             float *w_in = wgrad;
@@ -543,7 +547,7 @@ size_t fwd_smem(const Shape &sh) {
 }
 size_t bwd_smem(const Shape &sh) {
     return 1024 + (size_t)sh.kt_in * kWTileBytes + (size_t)sh.n_hid * kWTileBytes + 2048 +
-           (size_t)kWG * (2 + sh.n_hid + 1 + sh.kt_in) * kTileBytes + 64;
+           (size_t)kWG * (1 + sh.n_hid + 1 + sh.kt_in) * kTileBytes + 64;
 }
 
 int sm_count() {
@@ -559,17 +563,18 @@ int sm_count() {
 
 template <bool kSave>
 int launch_fwd(const void *inputs, const void *weights, uint32_t B, const Shape &sh, void *fbuf, void *outputs,
-               cudaStream_t st) {
+               const int32_t *n_active, cudaStream_t st) {
     const size_t smem = fwd_smem(sh);
     auto kern = k_ffmlp_fwd<kSave>;
+    if (smem > 200 * 1024) return LNB_ERR_UNSUPPORTED;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     size_t per_sm = (227 * 1024) / (smem + 1024);
     per_sm = per_sm < 1 ? 1 : (per_sm > 4 ? 4 : per_sm);   // 4 x 128 TMEM columns per SM
     const uint32_t cap = (uint32_t)per_sm * (uint32_t)sm_count();
     const uint32_t grid = (B / kRows) < cap ? (B / kRows) : cap;
     kern<<<grid, kThreads, smem, st>>>(static_cast<const __half *>(inputs), static_cast<const __half *>(weights), B, sh,
-                                      static_cast<__half *>(fbuf), static_cast<__half *>(outputs));
+                                      static_cast<__half *>(fbuf), static_cast<__half *>(outputs), n_active);
     count_launch();
     return launch_status();
 }
@@ -589,7 +594,20 @@ int lnb_ffmlp_forward(const void *inputs, const void *weights, uint32_t B, uint3
     int rc = check_shape(B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh);
     if (rc != LNB_OK) return rc;
     if (B == 0) return LNB_OK;
-    return launch_fwd<true>(inputs, weights, B, sh, forward_buffer, outputs, as_stream(stream));
+    return launch_fwd<true>(inputs, weights, B, sh, forward_buffer, outputs, nullptr, as_stream(stream));
+}
+
+int lnb_ffmlp_forward_ex(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                         uint32_t output_activation, void *forward_buffer, void *outputs, const int32_t *n_active,
+                         lnb_stream_t stream) {
+    if (!inputs || !weights || !outputs) return LNB_ERR_INVALID_ARGUMENT;
+    Shape sh;
+    int rc = check_shape(B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh);
+    if (rc != LNB_OK) return rc;
+    if (B == 0) return LNB_OK;
+    if (forward_buffer) return launch_fwd<true>(inputs, weights, B, sh, forward_buffer, outputs, n_active, as_stream(stream));
+    return launch_fwd<false>(inputs, weights, B, sh, nullptr, outputs, n_active, as_stream(stream));
 }
 
 int lnb_ffmlp_inference(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
@@ -601,7 +619,7 @@ int lnb_ffmlp_inference(const void *inputs, const void *weights, uint32_t B, uin
     int rc = check_shape(B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh);
     if (rc != LNB_OK) return rc;
     if (B == 0) return LNB_OK;
-    return launch_fwd<false>(inputs, weights, B, sh, nullptr, outputs, as_stream(stream));
+    return launch_fwd<false>(inputs, weights, B, sh, nullptr, outputs, nullptr, as_stream(stream));
 }
 
 size_t lnb_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_dim, uint32_t hidden_dim,
@@ -612,18 +630,18 @@ size_t lnb_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_di
 
 static int ffmlp_backward_impl(const void *grad, const void *inputs, const void *weights, const void *forward_buffer,
                                uint32_t B, const Shape &sh, int calc_grad_inputs, void *backward_buffer,
-                               void *grad_inputs, float *wgrad_f32, cudaStream_t st) {
+                               void *grad_inputs, float *wgrad_f32, const int32_t *n_active, cudaStream_t st) {
     const size_t smem = bwd_smem(sh);
+    if (smem > 200 * 1024) return LNB_ERR_UNSUPPORTED;   // num_layers too deep for the two-tile backward
     cudaError_t e = cudaFuncSetAttribute(k_ffmlp_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    if (smem > 227 * 1024) return LNB_ERR_UNSUPPORTED;
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     const uint32_t cap = (uint32_t)sm_count();   // 512 TMEM columns: one CTA per SM, two row tiles in flight each
     const uint32_t pairs = (B / kRows + kWG - 1) / kWG;
     const uint32_t grid = pairs < cap ? pairs : cap;
     k_ffmlp_bwd<<<grid, kBwdThreads, smem, st>>>(
         static_cast<const __half *>(grad), static_cast<const __half *>(inputs), static_cast<const __half *>(weights),
         static_cast<const __half *>(forward_buffer), B, sh, static_cast<__half *>(backward_buffer),
-        calc_grad_inputs ? static_cast<__half *>(grad_inputs) : nullptr, wgrad_f32);
+        calc_grad_inputs ? static_cast<__half *>(grad_inputs) : nullptr, wgrad_f32, n_active);
     count_launch();
     return launch_status();
 }
@@ -646,7 +664,7 @@ int lnb_ffmlp_backward(const void *grad, const void *inputs, const void *weights
     cudaError_t e = cudaMemsetAsync(workspace, 0, need, st);
     if (e != cudaSuccess) return (int)e;
     rc = ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, backward_buffer,
-                             grad_inputs, static_cast<float *>(workspace), st);
+                             grad_inputs, static_cast<float *>(workspace), nullptr, st);
     if (rc != LNB_OK) return rc;
     if (grad_weights) {
         const size_t n = need / sizeof(float);
@@ -662,7 +680,7 @@ int lnb_ffmlp_backward_accumulate(const void *grad, const void *inputs, const vo
                                   const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
                                   uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
                                   uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
-                                  float *grad_weights_f32, lnb_stream_t stream) {
+                                  float *grad_weights_f32, const int32_t *n_active, lnb_stream_t stream) {
     if (!grad || !inputs || !weights || !forward_buffer || !grad_weights_f32) return LNB_ERR_INVALID_ARGUMENT;
     if (calc_grad_inputs && !grad_inputs) return LNB_ERR_INVALID_ARGUMENT;
     Shape sh;
@@ -670,7 +688,7 @@ int lnb_ffmlp_backward_accumulate(const void *grad, const void *inputs, const vo
     if (rc != LNB_OK) return rc;
     if (B == 0) return LNB_OK;
     return ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, nullptr, grad_inputs,
-                               grad_weights_f32, as_stream(stream));
+                               grad_weights_f32, n_active, as_stream(stream));
 }
 
 int lnb_allocate_splitk(size_t size) {

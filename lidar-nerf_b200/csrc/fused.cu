@@ -20,7 +20,7 @@ __global__ void __launch_bounds__(kThreads)
 k_zero_tail(float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
             const int32_t *__restrict__ counter, uint32_t M) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= M) return;
+    if (i >= active_rows(M, counter)) return;      // only up to the end of the last partially filled 128-row tile
     const uint32_t used = (uint32_t)max(counter[0], 0);
     if (i < used) return;
     xyzs[i * 3] = xyzs[i * 3 + 1] = xyzs[i * 3 + 2] = 0.f;
@@ -36,8 +36,11 @@ k_zero_tail(float *__restrict__ xyzs, float *__restrict__ dirs, float *__restric
 constexpr int kHeadRows = 128;
 __global__ void __launch_bounds__(kHeadRows)
 k_head_input(const __half *__restrict__ sigma_out, const float *__restrict__ dirs, uint32_t M, uint32_t deg,
-             uint32_t in_pad, float density_scale, float *__restrict__ sigma, __half *__restrict__ head_in) {
+             uint32_t in_pad, float density_scale, float *__restrict__ sigma, __half *__restrict__ head_in,
+             const int32_t *__restrict__ n_active) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    M = active_rows(M, n_active);
+    if (blockIdx.x * kHeadRows >= M) return;
     __half *tile = reinterpret_cast<__half *>(smem_raw);          // [kHeadRows][in_pad + 8] (padded rows)
     const uint32_t pitch = in_pad + 8;
     const uint32_t s0 = blockIdx.x * kHeadRows;
@@ -81,9 +84,10 @@ k_head_input(const __half *__restrict__ sigma_out, const float *__restrict__ dir
 
 // LiDAR head output -> (ray-drop, intensity) = sigmoid(h[0:2])   (network.py:230)
 __global__ void __launch_bounds__(kThreads)
-k_head_rgb(const __half *__restrict__ head_out, uint32_t M, float *__restrict__ rgb) {
+k_head_rgb(const __half *__restrict__ head_out, uint32_t M, float *__restrict__ rgb,
+           const int32_t *__restrict__ n_active) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= M) return;
+    if (s >= active_rows(M, n_active)) return;
     const __half2 h = *reinterpret_cast<const __half2 *>(head_out + (size_t)s * 16);
     const float2 f = __half22float2(h);
     reinterpret_cast<float2 *>(rgb)[s] = make_float2(1.f / (1.f + __expf(-f.x)), 1.f / (1.f + __expf(-f.y)));
@@ -123,9 +127,9 @@ k_lidar_loss(const float *__restrict__ ws, const float *__restrict__ depth, cons
 // d loss / d head_out = [ g_rgb * s (1 - s), 0 ... 0 ]  (fp16 row of 16)
 __global__ void __launch_bounds__(kThreads)
 k_head_out_grad(const float *__restrict__ g_rgb, const float *__restrict__ rgb, uint32_t M,
-                __half *__restrict__ g_head_out) {
+                __half *__restrict__ g_head_out, const int32_t *__restrict__ n_active) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= M) return;
+    if (s >= active_rows(M, n_active)) return;
     const float2 g = reinterpret_cast<const float2 *>(g_rgb)[s];
     const float2 p = reinterpret_cast<const float2 *>(rgb)[s];
     uint4 lo = make_uint4(pack2(g.x * p.x * (1.f - p.x), g.y * p.y * (1.f - p.y)), 0, 0, 0);
@@ -138,9 +142,9 @@ k_head_out_grad(const float *__restrict__ g_rgb, const float *__restrict__ rgb, 
 __global__ void __launch_bounds__(kThreads)
 k_sigma_out_grad(const float *__restrict__ g_sigma, const __half *__restrict__ sigma_out,
                  const __half *__restrict__ g_head_in, uint32_t M, uint32_t in_pad, uint32_t enc_dim,
-                 float density_scale, __half *__restrict__ g_sigma_out) {
+                 float density_scale, __half *__restrict__ g_sigma_out, const int32_t *__restrict__ n_active) {
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-    if (s >= M) return;
+    if (s >= active_rows(M, n_active)) return;
     const float h0 = __half2float(sigma_out[(size_t)s * 16]);
     const float g0 = g_sigma[s] * density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));   // activation.py:14-17
     const __half *gi = g_head_in + (size_t)s * in_pad + enc_dim;
@@ -192,7 +196,8 @@ int lnb_zero_sample_tail(float *xyzs, float *dirs, float *deltas, const int32_t 
 }
 
 int lnb_field_head_input(const void *sigma_out, const float *dirs, uint32_t M, uint32_t degree, uint32_t in_pad,
-                         float density_scale, float *sigma, void *head_in, lnb_stream_t stream) {
+                         float density_scale, float *sigma, void *head_in, const int32_t *n_active,
+                         lnb_stream_t stream) {
     if (!sigma_out || !dirs || !sigma || !head_in) return LNB_ERR_INVALID_ARGUMENT;
     if (in_pad % 8 != 0 || in_pad < 3 + 6 * degree + 15) return LNB_ERR_INVALID_ARGUMENT;
     if (M == 0) return LNB_OK;
@@ -200,15 +205,15 @@ int lnb_field_head_input(const void *sigma_out, const float *dirs, uint32_t M, u
     if (smem > 48 * 1024) return LNB_ERR_UNSUPPORTED;
     k_head_input<<<(M + kHeadRows - 1) / kHeadRows, kHeadRows, smem, as_stream(stream)>>>(
         static_cast<const __half *>(sigma_out), dirs, M, degree, in_pad, density_scale, sigma,
-        static_cast<__half *>(head_in));
+        static_cast<__half *>(head_in), n_active);
     count_launch();
     return launch_status();
 }
 
-int lnb_field_head_rgb(const void *head_out, uint32_t M, float *rgb, lnb_stream_t stream) {
+int lnb_field_head_rgb(const void *head_out, uint32_t M, float *rgb, const int32_t *n_active, lnb_stream_t stream) {
     if (!head_out || !rgb) return LNB_ERR_INVALID_ARGUMENT;
     if (M == 0) return LNB_OK;
-    k_head_rgb<<<nblk(M), kThreads, 0, as_stream(stream)>>>(static_cast<const __half *>(head_out), M, rgb);
+    k_head_rgb<<<nblk(M), kThreads, 0, as_stream(stream)>>>(static_cast<const __half *>(head_out), M, rgb, n_active);
     count_launch();
     return launch_status();
 }
@@ -227,22 +232,22 @@ int lnb_lidar_loss(const float *weights_sum, const float *depth, const float *im
 }
 
 int lnb_field_head_out_grad(const float *g_rgb, const float *rgb, uint32_t M, void *g_head_out,
-                            lnb_stream_t stream) {
+                            const int32_t *n_active, lnb_stream_t stream) {
     if (!g_rgb || !rgb || !g_head_out) return LNB_ERR_INVALID_ARGUMENT;
     if (M == 0) return LNB_OK;
-    k_head_out_grad<<<nblk(M), kThreads, 0, as_stream(stream)>>>(g_rgb, rgb, M, static_cast<__half *>(g_head_out));
+    k_head_out_grad<<<nblk(M), kThreads, 0, as_stream(stream)>>>(g_rgb, rgb, M, static_cast<__half *>(g_head_out), n_active);
     count_launch();
     return launch_status();
 }
 
 int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const void *g_head_in, uint32_t M,
                              uint32_t in_pad, uint32_t degree, float density_scale, void *g_sigma_out,
-                             lnb_stream_t stream) {
+                             const int32_t *n_active, lnb_stream_t stream) {
     if (!g_sigma || !sigma_out || !g_head_in || !g_sigma_out) return LNB_ERR_INVALID_ARGUMENT;
     if (M == 0) return LNB_OK;
     k_sigma_out_grad<<<nblk(M), kThreads, 0, as_stream(stream)>>>(
         g_sigma, static_cast<const __half *>(sigma_out), static_cast<const __half *>(g_head_in), M, in_pad,
-        3 + 6 * degree, density_scale, static_cast<__half *>(g_sigma_out));
+        3 + 6 * degree, density_scale, static_cast<__half *>(g_sigma_out), n_active);
     count_launch();
     return launch_status();
 }

@@ -134,8 +134,10 @@ __global__ void __launch_bounds__(kFwdThreads)
 k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
            const int32_t *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
            float S, uint32_t H, T *__restrict__ dy_dx, uint32_t gridtype, bool align_corners,
-           uint32_t interp, int layout, float2 norm) {
+           uint32_t interp, int layout, float2 norm, const int32_t *__restrict__ n_active) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    B = (layout == LNB_LAYOUT_LBC) ? B : active_rows(B, n_active);   // [L,B,C] addressing needs the true B
+    if (blockIdx.x * kTileB >= B) return;
     T *tile = reinterpret_cast<T *>(smem_raw);  // [kTileB][pitch], only for LNB_LAYOUT_BLC
     const uint32_t F = L * C;
     const uint32_t pitch = F + (sizeof(T) == 2 ? 2 : 1);
@@ -287,11 +289,13 @@ __global__ void __launch_bounds__(kBwdThreads)
 k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
            const int32_t *__restrict__ offsets, TA *__restrict__ grad_table, uint32_t B, uint32_t L,
            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout, float2 norm,
-           uint32_t level_begin) {
+           uint32_t level_begin, const int32_t *__restrict__ n_active) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t level = level_begin + blockIdx.y;
+    const uint32_t Bact = active_rows(B, n_active);
+    if (blockIdx.x * blockDim.x >= Bact) return;
     const LevelGeo g = level_geo(offsets, level, S, H);
-    const bool in_range = b < B;
+    const bool in_range = b < Bact;
     if (!kAgg && !in_range) return;
     Cell<D> cell;
     if (in_range) cell = locate<D>(inputs + (size_t)b * D, g, align_corners, interp, norm);
@@ -300,7 +304,7 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
 #pragma unroll
         for (uint32_t d = 0; d < D; ++d) cell.base[d] = 0, cell.frac[d] = 0.f;
     }
-    const bool live = in_range && cell.inside;
+    bool live = in_range && cell.inside;
     if (!kAgg && !live) return;
 
     float gv[C];
@@ -309,9 +313,17 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
     if (live) {
         const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * C
                                                   : grad + ((size_t)b * L + level) * C;
+        bool any = false;
 #pragma unroll
-        for (uint32_t c = 0; c < C; ++c) gv[c] = Num<TG>::to_f(gp[c]);
+        for (uint32_t c = 0; c < C; ++c) {
+            gv[c] = Num<TG>::to_f(gp[c]);
+            any |= (gv[c] != 0.f);
+        }
+        // a zero gradient row adds nothing: skip its 2^D atomics.  (Padding samples all sit at one position and
+        // would otherwise serialise tens of thousands of atomics on the same 2^D rows of every level.)
+        live = any;
     }
+    if (!kAgg && !live) return;
 
     // run structure (shared by all corners): head = first lane of a run of identical cells
     unsigned lane = 0, run_start = 0;
@@ -412,7 +424,7 @@ inline uint32_t agg_max_resolution() {
 template <typename T, uint32_t D, uint32_t C>
 int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *out, uint32_t B,
             uint32_t L, float S, uint32_t H, void *dy_dx, uint32_t gridtype, bool ac, uint32_t interp,
-            int layout, float2 norm, cudaStream_t st) {
+            int layout, float2 norm, const int32_t *n_active, cudaStream_t st) {
     const uint32_t F = L * C;
     const size_t smem = (layout == LNB_LAYOUT_BLC)
                             ? (size_t)kTileB * (F + (sizeof(T) == 2 ? 2 : 1)) * sizeof(T) : 0;
@@ -423,7 +435,7 @@ int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *
     const unsigned threads = (L >= 16) ? kFwdThreads : max(32u, min((unsigned)kFwdThreads, L * 32u));
     kern<<<ceil_div<uint32_t>(B, kTileB), threads, smem, st>>>(
         inputs, static_cast<const T *>(emb), offsets, static_cast<T *>(out), B, L, S, H,
-        static_cast<T *>(dy_dx), gridtype, ac, interp, layout, norm);
+        static_cast<T *>(dy_dx), gridtype, ac, interp, layout, norm, n_active);
     count_launch();
     return launch_status();
 }
@@ -431,7 +443,7 @@ int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *
 template <typename T, uint32_t D, uint32_t C>
 int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void *grad_emb, uint32_t B,
             uint32_t L, float S, uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
-            bool ac, uint32_t interp, int layout, float2 norm, bool acc_f32, cudaStream_t st) {
+            bool ac, uint32_t interp, int layout, float2 norm, bool acc_f32, const int32_t *n_active, cudaStream_t st) {
     // leading (coarse) levels with resolution <= agg_max_res use the run-aggregating variant
     uint32_t n_agg = 0;
     {
@@ -446,7 +458,7 @@ int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void 
 #define LNB_BWD_LAUNCH(TA_, AGG_, NL_, L0_)                                                                       \
     k_grid_bwd<T, TA_, D, C, AGG_><<<dim3(bx, NL_), kBwdThreads, 0, st>>>(                                         \
         static_cast<const T *>(grad), inputs, offsets, static_cast<TA_ *>(grad_emb), B, L, S, H, gridtype, ac,    \
-        interp, layout, norm, L0_)
+        interp, layout, norm, L0_, n_active)
     if (acc_f32 && sizeof(T) == 2) {
         if (n_agg) { LNB_BWD_LAUNCH(float, true, n_agg, 0u); count_launch(); }
         if (n_agg < L) { LNB_BWD_LAUNCH(float, false, L - n_agg, n_agg); count_launch(); }
@@ -520,7 +532,8 @@ static float2 make_norm(float bound) {
 int lnb_grid_encode_forward_ex(const float *inputs, const void *embeddings, const int32_t *offsets,
                                void *outputs, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S,
                                uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners,
-                               uint32_t interp, int dtype, int layout, float in_bound, lnb_stream_t stream) {
+                               uint32_t interp, int dtype, int layout, float in_bound,
+                               const int32_t *n_active, lnb_stream_t stream) {
     if (!inputs || !embeddings || !offsets || !outputs) return LNB_ERR_INVALID_ARGUMENT;
     if (gridtype > 1 || interp > 1 || (layout != LNB_LAYOUT_LBC && layout != LNB_LAYOUT_BLC) || L == 0)
         return LNB_ERR_INVALID_ARGUMENT;
@@ -529,7 +542,7 @@ int lnb_grid_encode_forward_ex(const float *inputs, const void *embeddings, cons
     const bool ac = align_corners != 0;
     const float2 norm = make_norm(in_bound);
     LNB_GRID_DISPATCH(run_fwd, inputs, embeddings, offsets, outputs, B, L, S, H, dy_dx, gridtype, ac,
-                      interp, layout, norm, st);
+                      interp, layout, norm, n_active, st);
 }
 
 int lnb_grid_encode_forward(const float *inputs, const void *embeddings, const int32_t *offsets,
@@ -537,7 +550,7 @@ int lnb_grid_encode_forward(const float *inputs, const void *embeddings, const i
                             uint32_t H, void *dy_dx, uint32_t gridtype, int align_corners,
                             uint32_t interp, int dtype, int layout, lnb_stream_t stream) {
     return lnb_grid_encode_forward_ex(inputs, embeddings, offsets, outputs, B, D, C, L, S, H, dy_dx, gridtype,
-                                      align_corners, interp, dtype, layout, 0.f, stream);
+                                      align_corners, interp, dtype, layout, 0.f, nullptr, stream);
 }
 
 int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const void *embeddings,
@@ -545,7 +558,7 @@ int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const voi
                                 uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx,
                                 void *grad_inputs, uint32_t gridtype, int align_corners,
                                 uint32_t interp, int dtype, int layout, float in_bound,
-                                int accumulate_f32, lnb_stream_t stream) {
+                                int accumulate_f32, const int32_t *n_active, lnb_stream_t stream) {
     (void)embeddings;  // the table values are not needed for the table gradient (kept for ABI parity)
     if (!grad || !inputs || !offsets || !grad_embeddings) return LNB_ERR_INVALID_ARGUMENT;
     if (gridtype > 1 || interp > 1 || (layout != LNB_LAYOUT_LBC && layout != LNB_LAYOUT_BLC) || L == 0)
@@ -557,7 +570,7 @@ int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const voi
     const float2 norm = make_norm(in_bound);
     const bool acc32 = accumulate_f32 != 0;
     LNB_GRID_DISPATCH(run_bwd, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs,
-                      gridtype, ac, interp, layout, norm, acc32, st);
+                      gridtype, ac, interp, layout, norm, acc32, n_active, st);
 }
 
 int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings,
@@ -567,7 +580,7 @@ int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *
                              uint32_t interp, int dtype, int layout, lnb_stream_t stream) {
     return lnb_grid_encode_backward_ex(grad, inputs, embeddings, offsets, grad_embeddings, B, D, C, L, S, H,
                                        dy_dx, grad_inputs, gridtype, align_corners, interp, dtype, layout, 0.f, 0,
-                                       stream);
+                                       nullptr, stream);
 }
 
 }  // extern "C"

@@ -197,17 +197,23 @@ class LidarFieldEngine:
         rm.march_rays_train(self.rays_o, self.rays_d, self.bitfield, c.bound, c.dt_gamma, c.max_steps, N, c.cascade,
                             c.grid_size, M, self.nears, self.fars, self.xyzs, self.dirs, self.deltas, self.rays,
                             self.counter, self.noises)
-        _ck(lib.lnb_zero_sample_tail(p(self.xyzs), p(self.dirs), p(self.deltas), p(self.counter), u32(M), s), "zero_tail")
+        # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
+        # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
+        na = p(self.counter)
+        _ck(lib.lnb_zero_sample_tail(p(self.xyzs), p(self.dirs), p(self.deltas), na, u32(M), s), "zero_tail")
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
-                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), s), "grid_fwd")
-        ff.ffmlp_forward(self.enc, self.w_sigma_h, M, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6,
-                         self.fb_sigma, self.sig_out)
+                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
+            "grid_fwd")
+        _ck(lib.lnb_ffmlp_forward_ex(p(self.enc), p(self.w_sigma_h), u32(M), u32(self.enc_dim), u32(16),
+                                     u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), p(self.fb_sigma),
+                                     p(self.sig_out), na, s), "ffmlp_fwd(sigma)")
         _ck(lib.lnb_field_head_input(p(self.sig_out), p(self.dirs), u32(M), u32(c.freq_degree), u32(c.head_in_dim),
-                                     f32(c.density_scale), p(self.sigma), p(self.head_in), s), "head_input")
-        ff.ffmlp_forward(self.head_in, self.w_head_h, M, c.head_in_dim, 16, c.hidden_dim, c.head_layers, 0, 6,
-                         self.fb_head, self.head_out)
-        _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), s), "head_rgb")
+                                     f32(c.density_scale), p(self.sigma), p(self.head_in), na, s), "head_input")
+        _ck(lib.lnb_ffmlp_forward_ex(p(self.head_in), p(self.w_head_h), u32(M), u32(c.head_in_dim), u32(16),
+                                     u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), p(self.fb_head),
+                                     p(self.head_out), na, s), "ffmlp_fwd(head)")
+        _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), na, s), "head_rgb")
         rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2, self.ws,
                                            self.depth, self.image)
         _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N), f32(c.alpha_d),
@@ -219,22 +225,22 @@ class LidarFieldEngine:
         rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb, self.deltas,
                                             self.rays, self.ws, self.depth, self.image, M, N, c.T_thresh, 2,
                                             self.g_sigma, self.g_rgb)
-        _ck(lib.lnb_field_head_out_grad(p(self.g_rgb), p(self.rgb), u32(M), p(self.g_head_out), s), "head_out_grad")
+        _ck(lib.lnb_field_head_out_grad(p(self.g_rgb), p(self.rgb), u32(M), p(self.g_head_out), na, s), "head_out_grad")
         _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_head_out), p(self.head_in), p(self.w_head_h), p(self.fb_head),
                                               u32(M), u32(c.head_in_dim), u32(16), u32(c.hidden_dim),
                                               u32(c.head_layers), u32(0), u32(6), i32(1), p(self.g_head_in),
-                                              p(self.g_head_w), s), "ffmlp_bwd(head)")
+                                              p(self.g_head_w), na, s), "ffmlp_bwd(head)")
         _ck(lib.lnb_field_sigma_out_grad(p(self.g_sigma), p(self.sig_out), p(self.g_head_in), u32(M),
                                          u32(c.head_in_dim), u32(c.freq_degree), f32(c.density_scale),
-                                         p(self.g_sig_out), s), "sigma_out_grad")
+                                         p(self.g_sig_out), na, s), "sigma_out_grad")
         _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h), p(self.fb_sigma),
                                               u32(M), u32(self.enc_dim), u32(16), u32(c.hidden_dim),
                                               u32(c.sigma_layers), u32(0), u32(6), i32(1), p(self.g_enc),
-                                              p(self.g_sigma_w), s), "ffmlp_bwd(sigma)")
+                                              p(self.g_sigma_w), na, s), "ffmlp_bwd(sigma)")
         _ck(lib.lnb_grid_encode_backward_ex(p(self.g_enc), p(self.xyzs), p(self.table_h), p(self.offsets),
                                             p(self.g_table), u32(M), u32(3), u32(c.level_dim), u32(c.num_levels),
                                             f32(self.S), u32(c.base_resolution), vp(0), vp(0), u32(0), i32(0), u32(0),
-                                            i32(1), i32(1), f32(c.bound), i32(1), s), "grid_bwd")
+                                            i32(1), i32(1), f32(c.bound), i32(1), na, s), "grid_bwd")
 
     def _optimizer(self, lr=None):
         c = self.cfg
@@ -294,11 +300,12 @@ class LidarFieldEngine:
         cnt = self.counter.cpu()
         return int(cnt[0]), int(cnt[1])
 
-    def fit_sample_budget(self, headroom=1.15):
-        """Size M from the count of the last step (the reference's mean_count logic, raymarching.py:228-233)."""
+    def fit_sample_budget(self, headroom=1.5):
+        """Size M from the count of the last step (the role of the reference's mean_count, raymarching.py:228-233).
+        Kernels only process the produced rows, so generous headroom costs memory, not time."""
         produced, _ = self.samples_last_step()
         want = max(128, int(produced * headroom))
-        if want > self.M or want < 0.7 * self.M:
+        if produced > 0.9 * self.M or want < 0.4 * self.M:
             self._alloc_samples(want)
         return self.M
 
@@ -309,14 +316,15 @@ class LidarFieldEngine:
         return v
 
     # ---- occupancy grid --------------------------------------------------------------------------------------
-    def cell_centers(self, cas, jitter=True):
-        """World-space centres (optionally jittered inside the cell) of all H^3 cells of one cascade, in Morton
-        order (the layout packbits / the march expect)."""
+    def cell_centers(self, cas, idx=None, jitter=True):
+        """World-space centres (optionally jittered inside the cell) of the cells `idx` (Morton indices; all H^3 cells
+        if None) of one cascade - Morton order is the layout packbits / the march expect."""
+        from ..raymarching import morton3D_invert
         c = self.cfg
         H = c.grid_size
-        idx = torch.arange(H ** 3, dtype=torch.int32, device=self.dev)
-        from ..raymarching import morton3D_invert
-        coords = morton3D_invert(idx).float()                        # [H^3, 3] integer cell coordinates
+        if idx is None:
+            idx = torch.arange(H ** 3, dtype=torch.int32, device=self.dev)
+        coords = morton3D_invert(idx.int()).float()                  # [n, 3] integer cell coordinates
         xyz = 2 * coords / (H - 1) - 1                               # [-1, 1] (upstream convention)
         bound = min(2.0 ** cas, c.bound)
         half = bound / H
@@ -338,7 +346,8 @@ class LidarFieldEngine:
         p = lambda t: vp(t.data_ptr())   # noqa: E731
         _ck(lib.lnb_grid_encode_forward_ex(p(pts), p(self.table_h), p(self.offsets), p(enc), u32(Bp), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
-                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), s), "grid_fwd")
+                                           vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), vp(0), s),
+            "grid_fwd")
         out = torch.empty(Bp, 16, dtype=torch.float16, device=self.dev)
         ff.ffmlp_inference(enc, self.w_sigma_h, Bp, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6, None, out)
         return torch.exp(out[:B, 0].float()) * c.density_scale
@@ -353,24 +362,21 @@ class LidarFieldEngine:
         n_updates = self.step_count // max(c.grid_update_interval, 1)
         full = (n_updates <= 16) if full is None else full
         for cas in range(c.cascade):
-            xyz = self.cell_centers(cas)
             if full:
-                sel = None
-                sig = self.query_density(xyz)
+                sig = self.query_density(self.cell_centers(cas))
+                self.density_grid[cas] = torch.maximum(self.density_grid[cas] * decay, sig)
             else:   # H^3/4 uniform random cells + H^3/4 currently occupied cells
                 nq = H3 // 4
                 rnd = torch.randint(0, H3, (nq,), device=self.dev)
-                occ = torch.nonzero(self.density_grid[cas] > 0).squeeze(-1)
+                occ = torch.nonzero(torch.maximum(self.density_grid[cas], self.prior_grid[cas]) > 0).squeeze(-1)
                 if occ.numel() > 0:
                     occ = occ[torch.randint(0, occ.numel(), (nq,), device=self.dev)]
                     sel = torch.cat([rnd, occ])
                 else:
                     sel = rnd
-                sig = self.query_density(xyz[sel])
-            if sel is None:
-                self.density_grid[cas] = torch.maximum(self.density_grid[cas] * decay, sig)
-            else:
+                sig = self.query_density(self.cell_centers(cas, sel))
                 cur = self.density_grid[cas]
+                # duplicates in `sel` resolve to one of the candidate values, like torch-ngp's indexed assignment
                 cur[sel] = torch.maximum(cur[sel] * decay, sig)
         merged = torch.maximum(self.density_grid, self.prior_grid)
         self.mean_density = float(merged.clamp(min=0).mean().item())

@@ -414,7 +414,7 @@ def test_sh_encode(be, orc, deg):
         np.testing.assert_allclose(N_(dy), N_(dy2), rtol=1e-4, atol=2e-4)
 
 
-FFMLP = [(256, 32, 2), (384, 96, 2), (128, 64, 3), (128 * 300, 32, 2), (128, 16, 2), (256, 128, 4)]
+FFMLP = [(256, 32, 2), (384, 96, 2), (128, 64, 3), (128 * 300, 32, 2), (128, 16, 2), (256, 128, 2), (128 * 7, 96, 2)]
 
 
 @pytest.mark.parametrize("B,ind,nl", FFMLP)
@@ -457,6 +457,9 @@ def test_ffmlp_rejects_unsupported_shapes(be):
         be._ffmlp.ffmlp_forward(x, w, 128, 32, 16, 32, 2, 0, 6, fb, out)      # hidden 32 not built
     with pytest.raises(RuntimeError):
         be._ffmlp.ffmlp_forward(x.float(), w, 128, 32, 16, 64, 2, 0, 6, fb, out)  # dtype
+    # an unsupported call must not poison the next (valid) one
+    be._ffmlp.ffmlp_forward(x, w, 128, 32, 16, 64, 2, 0, 6, fb, out)
+    torch.cuda.synchronize()
 
 
 def test_adam_step(be, orc):
