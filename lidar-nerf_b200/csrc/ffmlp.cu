@@ -54,13 +54,11 @@ __device__ __forceinline__ void load_tiles(uint32_t tile0, uint32_t tile_stride,
         const uint32_t r = q / chunks_per_row, c = q - r * chunks_per_row;
         const uint32_t t = c >> 3, cc = c & 7;
         const uint32_t col = c * 8;
-        if (col < cols) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld + col));
-            sts128(tile_chunk_addr(tile0 + t * tile_stride, r, cc), v);
-        } else if (zero_pad) {
-            sts128(tile_chunk_addr(tile0 + t * tile_stride, r, cc), make_uint4(0, 0, 0, 0));
-        }
+        const uint32_t dst = tile_chunk_addr(tile0 + t * tile_stride, r, cc);
+        if (col < cols) cp_async16(dst, src + (size_t)r * ld + col);
+        else if (zero_pad) cp_async16(dst, src, 0);
     }
+    // asynchronous: the caller waits (cp_async_wait_all) before publishing the tile to the tensor core
 }
 
 // swizzled 128 x 64 tile -> global rows of 64 halves (128 B), fully coalesced (a warp writes 512 B).
@@ -132,6 +130,7 @@ k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t
         load_tiles(s_whid + l * kWTileBytes, kWTileBytes, W + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
                    kHid, false);
     load_tiles(s_wout, kWOutBytes, W + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid, false);
+    cp_async_wait_all();
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -143,10 +142,13 @@ k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t
 
     uint32_t phase = 0;
     const uint32_t n_tiles = active_rows(B, n_active) / kRows;   // B (the buffer stride) stays the full batch
+    // the input tile of the NEXT row tile is fetched (cp.async) as soon as the first-layer MMA has consumed the
+    // current one, so its HBM latency hides behind the remaining layers
+    if (blockIdx.x < n_tiles)
+        load_tiles(s_x, kTileBytes, X + (size_t)blockIdx.x * kRows * sh.in_dim, kRows, sh.in_dim, sh.in_dim, false);
     for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const size_t row0 = (size_t)tile * kRows;
-        // input tile -> smem
-        load_tiles(s_x, kTileBytes, X + row0 * sh.in_dim, kRows, sh.in_dim, sh.in_dim, false);
+        cp_async_wait_all();
         fence_proxy_async();
         fence_before_sync();
         __syncthreads();
@@ -164,6 +166,9 @@ k_ffmlp_fwd(const __half *__restrict__ X, const __half *__restrict__ W, uint32_t
             mbar_wait(s_bar, phase);
             phase ^= 1;
             fence_after_sync();
+            if (layer == 0 && tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's inputs
+                load_tiles(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * sh.in_dim, kRows, sh.in_dim,
+                           sh.in_dim, false);
             // epilogue: ReLU, fp16, back into the operand tile (row `row`)
 #pragma unroll
             for (uint32_t half_id = 0; half_id < 2; ++half_id) {
@@ -254,10 +259,8 @@ __device__ __forceinline__ void wg_load_tiles(uint32_t tid, uint32_t tile0, cons
     const uint32_t cpr = kt * 8;
     for (uint32_t q = tid; q < kRows * cpr; q += 128) {
         const uint32_t r = q / cpr, c = q - r * cpr;
-        if (c * 8 < cols) {
-            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld + c * 8));
-            sts128(tile_chunk_addr(tile0 + (c >> 3) * kTileBytes, r, c & 7), v);
-        }
+        if (c * 8 < cols)
+            cp_async16(tile_chunk_addr(tile0 + (c >> 3) * kTileBytes, r, c & 7), src + (size_t)r * ld + c * 8);
     }
 }
 __device__ __forceinline__ void wg_store_tile_rows(uint32_t tid, uint32_t tile, __half *__restrict__ dst) {
@@ -305,9 +308,9 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
             const uint32_t kt = (cols + 63) / 64, cpr = kt * 8;
             for (uint32_t q = t; q < rows * cpr; q += nthr) {
                 const uint32_t r = q / cpr, c = q - r * cpr;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (c * 8 < cols) v = __ldg(reinterpret_cast<const uint4 *>(src + (size_t)r * ld + c * 8));
-                sts128(tile_chunk_addr(tile0 + (c >> 3) * stride, r, c & 7), v);
+                const bool ok = c * 8 < cols;
+                cp_async16(tile_chunk_addr(tile0 + (c >> 3) * stride, r, c & 7), ok ? src + (size_t)r * ld + c * 8 : src,
+                           ok ? 16u : 0u);
             }
         };
         load_w(s_win, kWTileBytes, W, kHid, sh.in_dim, sh.in_dim);
@@ -315,6 +318,7 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
             load_w(s_whid + l * kWTileBytes, kWTileBytes, W + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid);
         load_w(s_wout, kWOutBytes, W + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid);
         for (uint32_t q = t; q < kWG * wg_bytes / 16; q += nthr) sts128(s_wg0 + q * 16, make_uint4(0, 0, 0, 0));
+        cp_async_wait_all();
     }
     fence_proxy_async();
     fence_before_sync();
@@ -388,13 +392,12 @@ k_ffmlp_bwd(const __half *__restrict__ G, const __half *__restrict__ X, const __
             // G: 16 valid columns (chunks 0,1); chunks 2..7 re-zeroed every tile because dH aliases this tile
             for (uint32_t q = tid; q < kRows * 8; q += 128) {
                 const uint32_t r = q >> 3, c = q & 7;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                if (c < 2) v = __ldg(reinterpret_cast<const uint4 *>(G + (row0 + r) * kOut + c * 8));
-                sts128(tile_chunk_addr(s_g, r, c), v);
+                cp_async16(tile_chunk_addr(s_g, r, c), G + (row0 + r) * kOut + (c < 2 ? c * 8 : 0), c < 2 ? 16u : 0u);
             }
             for (uint32_t l = 0; l < n_act; ++l)
                 wg_load_tiles(tid, s_h + l * kTileBytes, fbuf + ((size_t)l * B + row0) * kHid, kHid, kHid);
             wg_load_tiles(tid, s_x, X + row0 * sh.in_dim, sh.in_dim, sh.in_dim);
+            cp_async_wait_all();          // ~40 independent 16-byte copies per thread were in flight together
             fence_proxy_async();
             fence_before_sync();
             mbar_arrive(bar_ready);

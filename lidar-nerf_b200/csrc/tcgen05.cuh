@@ -32,6 +32,13 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
     return v;
 }
 
+// ---- asynchronous 16-byte global -> shared copies (LDGSTS): every chunk of a tile is in flight at once, no
+// register staging.  `bytes` < 16 zero-fills the remainder (bytes == 0 writes 16 zero bytes, src is not read).
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, uint32_t bytes = 16) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- proxies / fences ---------------------------------------------------------------------------
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads, bulk copies)
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }

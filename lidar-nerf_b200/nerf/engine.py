@@ -20,6 +20,7 @@ import torch
 from ..backend import (_raymarching as rm, _ffmlp as ff, adam_step)
 from .._lib import lib, check, u32, f32, i32, vp
 from ..gridencoder import level_offsets
+from . import dp
 
 
 @dataclass
@@ -246,17 +247,10 @@ class LidarFieldEngine:
         c = self.cfg
         self.step_count += 1
         adam_step(self.P, self.G, self.m, self.v, self.Ph, c.lr if lr is None else lr, c.beta1, c.beta2, c.eps,
-                  self.step_count, grad_scale=1.0 / (c.loss_scale * self._world()), zero_grad=True)
-
-    @staticmethod
-    def _world():
-        import torch.distributed as dist
-        return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+                  self.step_count, grad_scale=dp.grad_scale(c.loss_scale), zero_grad=True)
 
     def _allreduce(self):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.G)   # SUM; the 1/world factor is folded into Adam's grad_scale
+        dp.allreduce_gradient_(self.G)   # SUM over ranks; the 1/world factor is folded into Adam's grad_scale
 
     # ------------------------------------------------------------------------------------------------------
     def set_batch(self, rays_o, rays_d, gt):

@@ -1,0 +1,102 @@
+"""`NeRFNetwork` for the LiDAR field with the constructor/`density`/`color`/`get_params` contract of the reference's
+networks (lidarnerf/nerf/network.py:10-253, network_tcnn.py:10-211), wired the way SURVEY.md section 3.2 describes:
+hash grid -> FFMLP (sigma + 15 geo features) and [freq(dir) | geo] -> FFMLP (ray-drop, intensity), all on the sm_100a
+kernels.  `use_ffmlp=False` swaps the fused MLPs for bias-free nn.Linear stacks (the reference's network.py layout),
+which is what BASELINE config 1 (CPU plumbing) uses together with `encoding="frequency"`.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from ..activation import trunc_exp
+from ..encoding import get_encoder
+from .renderer import NeRFRenderer
+
+
+def _linear_stack(in_dim, hidden, out_dim, n_layers):
+    dims = [in_dim] + [hidden] * (n_layers - 1) + [out_dim]
+    return nn.ModuleList([nn.Linear(a, b, bias=False) for a, b in zip(dims[:-1], dims[1:])])
+
+
+def _run_stack(layers, h):
+    for i, lin in enumerate(layers):
+        h = lin(h)
+        if i != len(layers) - 1:
+            h = F.relu(h, inplace=True)
+    return h
+
+
+class NeRFNetwork(NeRFRenderer):
+    def __init__(self, encoding="hashgrid", encoding_dir="frequency", multires=15, desired_resolution=2048,
+                 log2_hashmap_size=19, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3,
+                 hidden_dim_color=64, out_color_dim=3, out_lidar_color_dim=2, bound=1, use_ffmlp=True, **kwargs):
+        super().__init__(bound, **kwargs)
+        self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
+        self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
+        self.out_color_dim, self.out_lidar_color_dim = out_color_dim, out_lidar_color_dim
+        self.use_ffmlp = use_ffmlp
+
+        if encoding == "frequency":
+            self.encoder, self.in_dim = get_encoder("frequency", multires=multires)
+        else:
+            self.encoder, self.in_dim = get_encoder(encoding, desired_resolution=desired_resolution,
+                                                    log2_hashmap_size=log2_hashmap_size)
+        self.encoder_dir, self.in_dim_dir = get_encoder("sphere_harmonics")
+        self.encoder_lidar_dir, self.in_dim_lidar_dir = get_encoder("frequency", multires=12)
+        raw_rgb, raw_lidar = self.in_dim_dir + geo_feat_dim, self.in_dim_lidar_dir + geo_feat_dim
+        if use_ffmlp:
+            from ..ffmlp import FFMLP
+            pad = lambda n: (n + 15) // 16 * 16   # noqa: E731
+            self.pad_in, self.pad_rgb, self.pad_lidar = pad(self.in_dim), pad(raw_rgb), pad(raw_lidar)
+            # FFMLP needs >= 3 matmuls: a num_layers-deep nn.Linear stack maps to max(num_layers - 1, 2) FFMLP layers
+            self.sigma_net = FFMLP(self.pad_in, 1 + geo_feat_dim, hidden_dim, max(num_layers, 2))
+            self.color_net = FFMLP(self.pad_rgb, out_color_dim, hidden_dim_color, max(num_layers_color - 1, 2))
+            self.lidar_color_net = FFMLP(self.pad_lidar, out_lidar_color_dim, hidden_dim_color,
+                                         max(num_layers_color - 1, 2))
+        else:
+            self.sigma_net = _linear_stack(self.in_dim, hidden_dim, 1 + geo_feat_dim, num_layers)
+            self.color_net = _linear_stack(raw_rgb, hidden_dim_color, out_color_dim, num_layers_color)
+            self.lidar_color_net = _linear_stack(raw_lidar, hidden_dim_color, out_lidar_color_dim, num_layers_color)
+
+    @staticmethod
+    def _pad(h, width):
+        return h if h.shape[-1] == width else F.pad(h, (0, width - h.shape[-1]))
+
+    def density(self, x):
+        h = self.encoder(x, bound=self.bound) if not isinstance(self.encoder, nn.Identity) else x
+        if self.use_ffmlp:
+            with torch.autocast("cuda", dtype=torch.float16):
+                h = self.sigma_net(self._pad(h, self.pad_in))
+        else:
+            h = _run_stack(self.sigma_net, h)
+        return {"sigma": trunc_exp(h[..., 0]), "geo_feat": h[..., 1:]}
+
+    def color(self, x, d, cal_lidar_color=False, mask=None, geo_feat=None, **kwargs):
+        out_dim = self.out_lidar_color_dim if cal_lidar_color else self.out_color_dim
+        if mask is not None:
+            rgbs = torch.zeros(mask.shape[0], out_dim, dtype=x.dtype, device=x.device)
+            if not mask.any():
+                return rgbs
+            d, geo_feat = d[mask], geo_feat[mask]
+        enc = self.encoder_lidar_dir(d) if cal_lidar_color else self.encoder_dir(d)
+        h = torch.cat([enc, geo_feat.to(enc.dtype)], dim=-1)
+        net = self.lidar_color_net if cal_lidar_color else self.color_net
+        if self.use_ffmlp:
+            with torch.autocast("cuda", dtype=torch.float16):
+                h = net(self._pad(h, self.pad_lidar if cal_lidar_color else self.pad_rgb))
+        else:
+            h = _run_stack(net, h)
+        h = torch.sigmoid(h.float())
+        if mask is None:
+            return h
+        rgbs[mask] = h.to(rgbs.dtype)
+        return rgbs
+
+    def forward(self, x, d):
+        dens = self.density(x)
+        return dens["sigma"], self.color(x, d, geo_feat=dens["geo_feat"])
+
+    def get_params(self, lr):
+        groups = [self.encoder, self.sigma_net, self.encoder_dir, self.color_net, self.encoder_lidar_dir,
+                  self.lidar_color_net]
+        return [{"params": list(m.parameters()), "lr": lr} for m in groups]
