@@ -271,6 +271,7 @@ def main():
     ms, ms_e2e = float(t[0]), float(t[1])
 
     # ---- per-kernel device times (eager pass, CUDA events on the launching stream) -> roofline of the dominant one ----
+    # (rank 0 only, collectives disabled inside; the other ranks wait at the final barrier)
     roof, kernels = None, None
     if rank == 0 and not args.no_profile:
         kernels, roof = profile_kernels(eng, pool, load)
@@ -296,8 +297,9 @@ def main():
         if world == 1 and not args.no_cpu_baseline:
             cb, _ = cpu_reference_leg(args, 1, args.cpu_rays, args.cpu_steps)
             out["cpu_baseline"] = cb
-        print(json.dumps(out))
+        print(json.dumps(out), flush=True)
     if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     return 0
 
@@ -368,6 +370,8 @@ def profile_kernels(eng, pool, load, iters=5):
     E.adam_step = adam_timed
     interval = eng.cfg.grid_update_interval
     eng.cfg.grid_update_interval = 0
+    real_allreduce = eng._allreduce
+    eng._allreduce = lambda: None      # rank-0-only pass: it must not issue collectives the other ranks do not join
     try:
         for i in range(iters + 1):
             load(pool[i % len(pool)])
@@ -378,6 +382,7 @@ def profile_kernels(eng, pool, load, iters=5):
             setattr(obj, name, fn)
         E.lib, E.adam_step = real_lib, real_adam
         eng.cfg.grid_update_interval = interval
+        eng._allreduce = real_allreduce
     us = {}
     for label in order:
         pairs = times[label]

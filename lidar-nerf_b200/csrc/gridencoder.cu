@@ -82,15 +82,24 @@ struct Cell {
 // GridEncoder.forward does in torch, (x + bound) / (2 bound) (grid.py:213; torch divides by a scalar by
 // multiplying with its fp32 reciprocal); norm.x == 0 means the inputs are already in [0,1].
 template <uint32_t D>
-__device__ __forceinline__ Cell<D> locate(const float *__restrict__ x, const LevelGeo &g,
-                                          bool align_corners, uint32_t interp, float2 norm) {
-    Cell<D> c;
-    c.inside = true;
+__device__ __forceinline__ bool load_unit_coords(const float *__restrict__ x, float2 norm, float (&v)[D]) {
+    bool inside = true;
 #pragma unroll
     for (uint32_t d = 0; d < D; ++d) {
-        const float v = (norm.x != 0.f) ? (x[d] + norm.x) * norm.y : x[d];
-        if (v < 0 || v > 1) c.inside = false;
-        float pos = v * g.scale + (align_corners ? 0.0f : 0.5f);
+        v[d] = (norm.x != 0.f) ? (x[d] + norm.x) * norm.y : x[d];
+        if (v[d] < 0 || v[d] > 1) inside = false;
+    }
+    return inside;
+}
+
+template <uint32_t D>
+__device__ __forceinline__ Cell<D> locate_unit(const float (&v)[D], bool inside, const LevelGeo &g,
+                                               bool align_corners, uint32_t interp) {
+    Cell<D> c;
+    c.inside = inside;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        float pos = v[d] * g.scale + (align_corners ? 0.0f : 0.5f);
         const float fl = floorf(pos);
         c.base[d] = (uint32_t)fl;
         pos -= (float)c.base[d];
@@ -103,6 +112,14 @@ __device__ __forceinline__ Cell<D> locate(const float *__restrict__ x, const Lev
         }
     }
     return c;
+}
+
+template <uint32_t D>
+__device__ __forceinline__ Cell<D> locate(const float *__restrict__ x, const LevelGeo &g,
+                                          bool align_corners, uint32_t interp, float2 norm) {
+    float v[D];
+    const bool inside = load_unit_coords<D>(x, norm, v);
+    return locate_unit<D>(v, inside, g, align_corners, interp);
 }
 
 template <typename T, uint32_t C>
@@ -130,7 +147,7 @@ __device__ __forceinline__ void load_row(const T *__restrict__ p, float (&v)[C])
 // Forward.  Accumulates in the table's type exactly like the reference (`scalar_t results[C]`,
 // gridencoder.cu:173-199): every `+= w * grid[...]` is rounded to T.
 template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(kFwdThreads)
+__global__ void __launch_bounds__(kFwdThreads, 3)
 k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
            const int32_t *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
            float S, uint32_t H, T *__restrict__ dy_dx, uint32_t gridtype, bool align_corners,
@@ -279,112 +296,121 @@ __device__ __forceinline__ void atomic_add_one(float *p, float a) { atomicAdd(p,
 // TG = type of the incoming gradient, TA = type of the table gradient (TA = float with TG = half is the
 // mixed mode of the fused training step: fp16 activations-grad, fp32 accumulation, no loss of small updates).
 //
-// kAgg: warp-level run aggregation for coarse levels.  Consecutive samples of a ray are a fraction of a cell apart
+// One thread owns one sample and walks all levels: the coordinates are loaded once and the gradient row (L*C values,
+// contiguous in the [B, L*C] layout) is read with 16-byte loads, instead of one dependent 4-byte load per
+// (sample, level) thread (the profile of the first version showed exactly those two loads as its top stalls).
+//
+// Levels below `n_agg` use warp-level run aggregation: consecutive samples of a ray are a fraction of a cell apart
 // on the coarse levels (37 samples per cell at level 0 of the KITTI config), so neighbouring lanes scatter into the
-// SAME 2^D rows and plain atomics serialise in L2 (measured: 1.8 ms for 425 k samples).  Lanes whose cell equals
-// the previous lane's cell form a run; the 2^D corner contributions are summed over the run with a segmented
-// shuffle scan and only the run's last lane issues the atomics (exact up to fp32 summation order).
-template <typename TG, typename TA, uint32_t D, uint32_t C, bool kAgg>
+// SAME 2^D rows and plain atomics serialise in L2.  Lanes whose cell equals the previous lane's cell form a run; the
+// 2^D corner contributions are summed over the run with a segmented shuffle scan and only the run's last lane issues
+// the atomics (exact up to fp32 summation order).  A zero gradient row adds nothing and is skipped (padding samples
+// all sit at one position and would otherwise serialise tens of thousands of atomics on the same rows).
+template <typename TG, typename TA, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(kBwdThreads)
 k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
            const int32_t *__restrict__ offsets, TA *__restrict__ grad_table, uint32_t B, uint32_t L,
            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout, float2 norm,
-           uint32_t level_begin, const int32_t *__restrict__ n_active) {
+           uint32_t n_agg, const int32_t *__restrict__ n_active) {
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t level = level_begin + blockIdx.y;
     const uint32_t Bact = active_rows(B, n_active);
     if (blockIdx.x * blockDim.x >= Bact) return;
-    const LevelGeo g = level_geo(offsets, level, S, H);
     const bool in_range = b < Bact;
-    if (!kAgg && !in_range) return;
-    Cell<D> cell;
-    if (in_range) cell = locate<D>(inputs + (size_t)b * D, g, align_corners, interp, norm);
+    const unsigned lane = lane_id();
+
+    float v[D];
+    bool inside = false;
+    if (in_range) inside = load_unit_coords<D>(inputs + (size_t)b * D, norm, v);
     else {
-        cell.inside = false;
 #pragma unroll
-        for (uint32_t d = 0; d < D; ++d) cell.base[d] = 0, cell.frac[d] = 0.f;
-    }
-    bool live = in_range && cell.inside;
-    if (!kAgg && !live) return;
-
-    float gv[C];
-#pragma unroll
-    for (uint32_t c = 0; c < C; ++c) gv[c] = 0.f;
-    if (live) {
-        const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * C
-                                                  : grad + ((size_t)b * L + level) * C;
-        bool any = false;
-#pragma unroll
-        for (uint32_t c = 0; c < C; ++c) {
-            gv[c] = Num<TG>::to_f(gp[c]);
-            any |= (gv[c] != 0.f);
-        }
-        // a zero gradient row adds nothing: skip its 2^D atomics.  (Padding samples all sit at one position and
-        // would otherwise serialise tens of thousands of atomics on the same 2^D rows of every level.)
-        live = any;
-    }
-    if (!kAgg && !live) return;
-
-    // run structure (shared by all corners): head = first lane of a run of identical cells
-    unsigned lane = 0, run_start = 0;
-    bool tail = true;
-    if (kAgg) {
-        lane = lane_id();
-        bool head = (lane == 0) || !live;
-        const int prev_live = __shfl_up_sync(kFullMask, (int)live, 1);
-        if (!prev_live) head = true;
-#pragma unroll
-        for (uint32_t d = 0; d < D; ++d) {
-            const uint32_t pb = __shfl_up_sync(kFullMask, cell.base[d], 1);
-            if (pb != cell.base[d]) head = true;
-        }
-        run_start = head ? lane : 0u;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned t = __shfl_up_sync(kFullMask, run_start, o);
-            if (lane >= (unsigned)o) run_start = max(run_start, t);
-        }
-        const int next_head = __shfl_down_sync(kFullMask, (int)head, 1);
-        tail = (lane == 31) || next_head;
+        for (uint32_t d = 0; d < D; ++d) v[d] = 0.f;
     }
 
-    TA *gt = grad_table + (size_t)g.table_offset * C;
+    for (uint32_t level = 0; level < L; ++level) {
+        const LevelGeo g = level_geo(offsets, level, S, H);
+        const Cell<D> cell = locate_unit<D>(v, inside, g, align_corners, interp);
+        float gv[C];
+        bool live = false;
 #pragma unroll
-    for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-        float w = 1;
-        uint32_t p[D];
+        for (uint32_t c = 0; c < C; ++c) gv[c] = 0.f;
+        if (in_range && inside) {
+            const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * C
+                                                      : grad + ((size_t)b * L + level) * C;
+            if constexpr (sizeof(TG) == 2 && C % 2 == 0) {
 #pragma unroll
-        for (uint32_t d = 0; d < D; ++d) {
-            if ((corner & (1u << d)) == 0) {
-                w *= 1 - cell.frac[d];
-                p[d] = cell.base[d];
+                for (uint32_t c = 0; c < C; c += 2) {
+                    const float2 f = __half22float2(__ldg(reinterpret_cast<const __half2 *>(gp + c)));
+                    gv[c] = f.x, gv[c + 1] = f.y;
+                }
             } else {
-                w *= cell.frac[d];
-                p[d] = cell.base[d] + 1;
-            }
-        }
-        float v[C];
 #pragma unroll
-        for (uint32_t c = 0; c < C; ++c) v[c] = w * gv[c];
-        if (kAgg) {
+                for (uint32_t c = 0; c < C; ++c) gv[c] = Num<TG>::to_f(__ldg(gp + c));
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) live |= (gv[c] != 0.f);
+        }
+        const bool agg = level < n_agg;      // warp-uniform
+        if (!agg && !live) continue;
+
+        unsigned run_start = 0;
+        bool tail = true;
+        if (agg) {
+            bool head = (lane == 0) || !live;
+            const int prev_live = __shfl_up_sync(kFullMask, (int)live, 1);
+            if (!prev_live) head = true;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                const uint32_t pb = __shfl_up_sync(kFullMask, cell.base[d], 1);
+                if (pb != cell.base[d]) head = true;
+            }
+            run_start = head ? lane : 0u;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) {
+                const unsigned t = __shfl_up_sync(kFullMask, run_start, o);
+                if (lane >= (unsigned)o) run_start = max(run_start, t);
+            }
+            const int next_head = __shfl_down_sync(kFullMask, (int)head, 1);
+            tail = (lane == 31) || next_head;
+        }
+
+        TA *gt = grad_table + (size_t)g.table_offset * C;
 #pragma unroll
-                for (uint32_t c = 0; c < C; ++c) {
-                    const float t = __shfl_up_sync(kFullMask, v[c], o);
-                    if (lane >= run_start + (unsigned)o) v[c] += t;
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            float w = 1;
+            uint32_t p[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                if ((corner & (1u << d)) == 0) {
+                    w *= 1 - cell.frac[d];
+                    p[d] = cell.base[d];
+                } else {
+                    w *= cell.frac[d];
+                    p[d] = cell.base[d] + 1;
                 }
             }
-            if (!(tail && live)) continue;
-        }
-        const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
-        TA *dst = gt + (size_t)row * C;
-        if constexpr (C % 2 == 0) {
+            float acc[C];
 #pragma unroll
-            for (uint32_t c = 0; c < C; c += 2) atomic_add_pair<TA>(dst + c, v[c], v[c + 1]);
-        } else {
+            for (uint32_t c = 0; c < C; ++c) acc[c] = w * gv[c];
+            if (agg) {
 #pragma unroll
-            for (uint32_t c = 0; c < C; ++c) atomic_add_one(dst + c, v[c]);
+                for (int o = 1; o < 32; o <<= 1) {
+#pragma unroll
+                    for (uint32_t c = 0; c < C; ++c) {
+                        const float t = __shfl_up_sync(kFullMask, acc[c], o);
+                        if (lane >= run_start + (unsigned)o) acc[c] += t;
+                    }
+                }
+                if (!(tail && live)) continue;
+            }
+            const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
+            TA *dst = gt + (size_t)row * C;
+            if constexpr (C % 2 == 0) {
+#pragma unroll
+                for (uint32_t c = 0; c < C; c += 2) atomic_add_pair<TA>(dst + c, acc[c], acc[c + 1]);
+            } else {
+#pragma unroll
+                for (uint32_t c = 0; c < C; ++c) atomic_add_one(dst + c, acc[c]);
+            }
         }
     }
 }
@@ -455,18 +481,15 @@ int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void 
         }
     }
     const unsigned bx = ceil_div<uint32_t>(B, kBwdThreads);
-#define LNB_BWD_LAUNCH(TA_, AGG_, NL_, L0_)                                                                       \
-    k_grid_bwd<T, TA_, D, C, AGG_><<<dim3(bx, NL_), kBwdThreads, 0, st>>>(                                         \
-        static_cast<const T *>(grad), inputs, offsets, static_cast<TA_ *>(grad_emb), B, L, S, H, gridtype, ac,    \
-        interp, layout, norm, L0_, n_active)
-    if (acc_f32 && sizeof(T) == 2) {
-        if (n_agg) { LNB_BWD_LAUNCH(float, true, n_agg, 0u); count_launch(); }
-        if (n_agg < L) { LNB_BWD_LAUNCH(float, false, L - n_agg, n_agg); count_launch(); }
-    } else {
-        if (n_agg) { LNB_BWD_LAUNCH(T, true, n_agg, 0u); count_launch(); }
-        if (n_agg < L) { LNB_BWD_LAUNCH(T, false, L - n_agg, n_agg); count_launch(); }
-    }
-#undef LNB_BWD_LAUNCH
+    if (acc_f32 && sizeof(T) == 2)
+        k_grid_bwd<T, float, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
+                                                               static_cast<float *>(grad_emb), B, L, S, H, gridtype,
+                                                               ac, interp, layout, norm, n_agg, n_active);
+    else
+        k_grid_bwd<T, T, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
+                                                           static_cast<T *>(grad_emb), B, L, S, H, gridtype, ac,
+                                                           interp, layout, norm, n_agg, n_active);
+    count_launch();
     int rc = launch_status();
     if (rc != LNB_OK) return rc;
     if (dy_dx) {

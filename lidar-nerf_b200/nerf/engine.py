@@ -283,7 +283,8 @@ class LidarFieldEngine:
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
         g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
+        # thread_local: other threads (e.g. NCCL's watchdog) may legally touch the CUDA API during the capture
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._forward_backward()
         self.G.zero_()   # capture does not execute, but keep the gradient clean regardless
         self._graph = g

@@ -196,10 +196,23 @@ def test_reference_shaped_network_trains_through_run_cuda():
     net = NeRFNetwork(encoding="hashgrid", desired_resolution=2048, log2_hashmap_size=15, bound=1,
                       min_near_lidar=seq.scale, density_thresh=10).to(DEV)
     net.train()
-    opt = torch.optim.Adam(net.get_params(1e-2), betas=(0.9, 0.99), eps=1e-15)
+    # LiDAR occupancy prior (cells containing GT returns, dilated by one) instead of the self-scheduled refresh:
+    # with only ~100 steps the randomly initialised density cannot carve free space on its own
+    from lidar_nerf_b200 import raymarching as rmw
+    pts = seq.surface_points()
+    H = net.grid_size
+    offs = torch.stack(torch.meshgrid(*([torch.arange(-1, 2, device=DEV)] * 3), indexing="ij"), -1).reshape(-1, 3)
+    cell = torch.clamp((0.5 * (pts + 1) * H).long(), 0, H - 1)
+    cell = torch.unique((cell[:, None, :] + offs[None]).reshape(-1, 3).clamp(0, H - 1), dim=0)
+    prior = torch.zeros(1, H ** 3, device=DEV)
+    prior[0, rmw.morton3D(cell.int()).long()] = 1.0
+    rmw.packbits(prior, 0.5, net.density_bitfield)
+    net.update_extra_state = lambda *a, **k: None
+    opt = torch.optim.Adam(net.get_params(5e-3), betas=(0.9, 0.99), eps=1e-15)
     gen = torch.Generator().manual_seed(0)
     losses = []
-    for it in range(30):
+    scale = 128.0            # static loss scale: the role GradScaler plays in the reference (nerf/utils.py:1221-1223)
+    for it in range(160):
         ro, rd, gt = seq.sample_batch(512, generator=gen, device=DEV)
         out = net.render(ro[None], rd[None], cal_lidar_color=True, staged=False, perturb=True, cuda_ray=True,
                          max_steps=256)
@@ -207,11 +220,15 @@ def test_reference_shaped_network_trains_through_run_cuda():
         loss = (1e3 * (out["depth_lidar"][0] * m - gt[:, 2] * m).abs() + (out["image_lidar"][0, :, 0] - m) ** 2
                 + 10 * (out["image_lidar"][0, :, 1] * m - gt[:, 1] * m) ** 2).mean()
         opt.zero_grad()
-        loss.backward()
+        (loss * scale).backward()
+        for grp in opt.param_groups:
+            for prm in grp["params"]:
+                if prm.grad is not None:
+                    prm.grad.div_(scale)
         opt.step()
-        losses.append(float(loss))
+        losses.append(float(loss.detach()))
     assert np.isfinite(losses).all(), losses
-    assert np.mean(losses[-5:]) < np.mean(losses[:5]), losses
+    assert np.mean(losses[-20:]) < 0.7 * np.mean(losses[:20]), (losses[:20], losses[-20:])
     assert net.encoder.embeddings.grad is not None and net.encoder.embeddings.grad.abs().sum() > 0
     # eval path: alive-ray loop with march_rays / composite_rays
     net.eval()
