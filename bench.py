@@ -33,7 +33,7 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=8)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
     ap.add_argument("--rays", type=int, default=RAYS)
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -223,6 +223,9 @@ def main():
     torch.cuda.synchronize()
     refresh_ms = r0.elapsed_time(r1)
 
+    if args.impl == "reference-cuda":
+        return reference_cuda_leg(args, eng, pool, load, world)
+
     def barrier():
         if world > 1:
             dist.barrier()
@@ -286,7 +289,7 @@ def main():
                           "samples_per_ray": produced / N, "sample_budget_M": eng.M, "params": eng.n_params,
                           "grid_refresh_ms": refresh_ms, "grid_refresh_every": cfg_interval,
                           "l2": "each step streams the 383 MB Adam state (> 126 MB L2); no explicit flush",
-                          "parallelism": f"dp{world} (NCCL allreduce of the flat fp32 gradient)" if world > 1 else "single"},
+                          "parallelism": f"dp{world} (NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params)" if world > 1 else "single"},
                "clocks": clk,
                "e2e": {"value": world * N * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                        "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4},
@@ -301,6 +304,43 @@ def main():
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+    return 0
+
+
+def reference_cuda_leg(args, eng, pool, load, world):
+    """Extra arm (not part of the driver contract): the same step wired from the UNMODIFIED reference CUDA extensions
+    in oracle/_ref (oracle/ref_cuda_step.py) on this GPU, same rays, same occupancy grid, same parameters; sample
+    buffers sized to the real sample count as the reference's mean_count logic does (raymarching.py:226-233)."""
+    import torch
+    from oracle.ref_cuda_step import RefCudaStep
+    if world > 1:
+        raise SystemExit("--impl reference-cuda is a single-GPU arm")
+    produced, _ = eng.samples_last_step()
+    eng.M = (int(produced * 1.05) + 127) // 128 * 128
+    ref = RefCudaStep(eng)
+    steps = min(args.steps, 30)
+
+    def run(n):
+        for i in range(n):
+            load(pool[i % len(pool)])
+            eng.noises.uniform_(0, 1)
+            ref.step(eng.rays_o, eng.rays_d, eng.gt, eng.noises)
+
+    run(3)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(steps)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / steps
+    out = {"impl": "reference-cuda", "metric": METRIC, "value": eng.N / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
+           "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
+           "dtype": "f16 tables+MLP (fp16 accumulate) / f32 march+composite / torch Adam",
+           "config": {"workload": WORKLOAD, "rays_per_gpu": eng.N, "sample_rows_M": eng.M,
+                      "note": "unmodified reference kernels (oracle/_ref) wired by oracle/ref_cuda_step.py the way the "
+                              "reference's Python wrappers call them; no autograd graph, no dataloader"}}
+    print(json.dumps(out), flush=True)
     return 0
 
 
@@ -370,8 +410,10 @@ def profile_kernels(eng, pool, load, iters=5):
     E.adam_step = adam_timed
     interval = eng.cfg.grid_update_interval
     eng.cfg.grid_update_interval = 0
-    real_allreduce = eng._allreduce
-    eng._allreduce = lambda: None      # rank-0-only pass: it must not issue collectives the other ranks do not join
+    real_ex = (eng.ex.reduce_scatter, eng.ex.all_gather)
+    # rank-0-only pass: it must not issue collectives the other ranks do not join
+    eng.ex.reduce_scatter = lambda full, out: out.copy_(full[eng.ex.lo:eng.ex.hi])
+    eng.ex.all_gather = lambda full, shard: full[eng.ex.lo:eng.ex.hi].copy_(shard)
     try:
         for i in range(iters + 1):
             load(pool[i % len(pool)])
@@ -382,7 +424,7 @@ def profile_kernels(eng, pool, load, iters=5):
             setattr(obj, name, fn)
         E.lib, E.adam_step = real_lib, real_adam
         eng.cfg.grid_update_interval = interval
-        eng._allreduce = real_allreduce
+        eng.ex.reduce_scatter, eng.ex.all_gather = real_ex
     us = {}
     for label in order:
         pairs = times[label]

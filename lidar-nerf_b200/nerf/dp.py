@@ -39,3 +39,36 @@ def shard_bounds(n, r, world):
 def rank_seed(base_seed):
     """Each rank draws its own rays: seed = base + rank."""
     return base_seed + rank()
+
+
+class ShardedExchange:
+    """Reduce-scatter -> (caller updates its shard) -> all-gather, over a flat vector padded to world * align.
+
+    The data-parallel step then moves 4 B/param (fp32 gradient reduce-scatter) + 2 B/param (fp16 parameter all-gather)
+    per rank instead of 8 B/param for a gradient all-reduce, and the optimiser touches 1/world of the Adam state.
+    """
+
+    def __init__(self, n, align=8):
+        self.world, self.rank = world_size(), rank()
+        unit = self.world * align
+        self.n = n
+        self.n_padded = (n + unit - 1) // unit * unit
+        self.shard = self.n_padded // self.world
+        self.lo = self.rank * self.shard
+        self.hi = self.lo + self.shard
+
+    def reduce_scatter(self, full_padded, out_shard):
+        """out_shard <- sum over ranks of full_padded[lo:hi]."""
+        if self.world == 1:
+            out_shard.copy_(full_padded[self.lo:self.hi])
+        else:
+            dist.reduce_scatter_tensor(out_shard, full_padded, op=dist.ReduceOp.SUM)
+        return out_shard
+
+    def all_gather(self, full_padded, shard):
+        """full_padded <- concatenation over ranks of `shard`."""
+        if self.world == 1:
+            full_padded[self.lo:self.hi].copy_(shard)
+        else:
+            dist.all_gather_into_tensor(full_padded, shard)
+        return full_padded

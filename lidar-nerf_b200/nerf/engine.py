@@ -98,21 +98,29 @@ class LidarFieldEngine:
         self.n_table, self.n_sigma, self.n_head = n_table, n_sigma, n_head
         n = n_table + n_sigma + n_head
         self.n_params = n
-        P = torch.empty(n, dtype=torch.float32)
+        self.ex = dp.ShardedExchange(n)                 # data-parallel layout of the flat vectors (1 rank: identity)
+        npad = self.ex.n_padded
+        P = torch.zeros(npad, dtype=torch.float32)
         P[:n_table].uniform_(-1e-4, 1e-4, generator=gen)                                   # grid.py:202-204
         bound_w = math.sqrt(3 / c.hidden_dim)                                              # ffmlp.py:242-245
-        P[n_table:].uniform_(-bound_w, bound_w, generator=gen)
-        self.P = P.to(dev)
-        self.G = torch.zeros(n, dtype=torch.float32, device=dev)
-        self.m = torch.zeros_like(self.G)
-        self.v = torch.zeros_like(self.G)
-        self.Ph = self.P.to(torch.float16)
+        P[n_table:n].uniform_(-bound_w, bound_w, generator=gen)
+        self.G = torch.zeros(npad, dtype=torch.float32, device=dev)
+        self.Ph = P.to(dev).to(torch.float16)
+        if self.ex.world > 1:
+            # fp32 master weights and Adam moments exist only for this rank's shard (1/world of 3 x 54.8 MB)
+            self.P = P[self.ex.lo:self.ex.hi].to(dev)
+            self.G_shard = torch.zeros(self.ex.shard, dtype=torch.float32, device=dev)
+            self.Ph_shard = torch.empty(self.ex.shard, dtype=torch.float16, device=dev)
+        else:
+            self.P = P.to(dev)
+        self.m = torch.zeros_like(self.P)
+        self.v = torch.zeros_like(self.P)
         self.table_h = self.Ph[:n_table].view(self.n_rows, c.level_dim)
         self.w_sigma_h = self.Ph[n_table:n_table + n_sigma]
-        self.w_head_h = self.Ph[n_table + n_sigma:]
+        self.w_head_h = self.Ph[n_table + n_sigma:n]
         self.g_table = self.G[:n_table]
         self.g_sigma_w = self.G[n_table:n_table + n_sigma]
-        self.g_head_w = self.G[n_table + n_sigma:]
+        self.g_head_w = self.G[n_table + n_sigma:n]
         self.step_count = 0
 
         # ---- occupancy state -------------------------------------------------------
@@ -244,13 +252,20 @@ class LidarFieldEngine:
                                             i32(1), i32(1), f32(c.bound), i32(1), na, s), "grid_bwd")
 
     def _optimizer(self, lr=None):
+        """Adam.  One rank: a single fused pass over the whole flat vector.  Data parallel: reduce-scatter the fp32
+        gradient, update only this rank's shard (fp32 master + moments live only here), all-gather the fp16 shadow."""
         c = self.cfg
         self.step_count += 1
-        adam_step(self.P, self.G, self.m, self.v, self.Ph, c.lr if lr is None else lr, c.beta1, c.beta2, c.eps,
-                  self.step_count, grad_scale=dp.grad_scale(c.loss_scale), zero_grad=True)
-
-    def _allreduce(self):
-        dp.allreduce_gradient_(self.G)   # SUM over ranks; the 1/world factor is folded into Adam's grad_scale
+        lr = c.lr if lr is None else lr
+        if self.ex.world == 1:
+            adam_step(self.P, self.G, self.m, self.v, self.Ph, lr, c.beta1, c.beta2, c.eps, self.step_count,
+                      grad_scale=1.0 / c.loss_scale, zero_grad=True)
+            return
+        self.ex.reduce_scatter(self.G, self.G_shard)
+        self.G.zero_()
+        adam_step(self.P, self.G_shard, self.m, self.v, self.Ph_shard, lr, c.beta1, c.beta2, c.eps, self.step_count,
+                  grad_scale=dp.grad_scale(c.loss_scale), zero_grad=False)
+        self.ex.all_gather(self.Ph, self.Ph_shard)
 
     # ------------------------------------------------------------------------------------------------------
     def set_batch(self, rays_o, rays_d, gt):
@@ -267,8 +282,8 @@ class LidarFieldEngine:
             self._graph.replay()          # march ... grid backward: one graph launch
         else:
             self._forward_backward()
-        self._allreduce()                 # data parallel: one NCCL all-reduce of the flat gradient (no-op for 1 GPU)
-        self._optimizer()                 # bias corrections change every step -> Adam stays outside the graph
+        self._optimizer()                 # Adam (+ the data-parallel exchange); bias corrections change every step,
+                                          # so it stays outside the graph
         if self.cfg.grid_update_interval > 0 and self.step_count % self.cfg.grid_update_interval == 0:
             self.update_density_grid()
 

@@ -40,6 +40,7 @@ def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2):
     P[:eng.n_table] = rng.uniform(-0.5, 0.5, size=eng.n_table).astype(np.float32)
     eng.P.copy_(torch.from_numpy(P))
     eng.Ph.copy_(eng.P.to(torch.float16))
+    P = P[:eng.n_params]
 
     eng.bitfield.copy_(torch.from_numpy(bitfield))
     eng.set_batch(torch.from_numpy(rays_o).to(device), torch.from_numpy(rays_d).to(device),
@@ -57,7 +58,7 @@ def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2):
     cpu = fs.field_step(params, rays_o, rays_d, gt, noises, bitfield, eng.M, level_scales=ls, apply_adam=False)
     rays = eng.rays.cpu().numpy()
     order = np.argsort(rays[:, 0])
-    gpu = dict(loss=float(eng.loss_acc.item()), grad=eng.G.cpu().numpy(), counts=rays[order, 2], ws=eng.ws.cpu().numpy(),
+    gpu = dict(loss=float(eng.loss_acc.item()), grad=eng.G[:eng.n_params].cpu().numpy(), counts=rays[order, 2], ws=eng.ws.cpu().numpy(),
                depth=eng.depth.cpu().numpy(), image=eng.image.cpu().numpy(), n_samples=int(eng.counter[0].item()))
     return eng, gpu, cpu
 

@@ -111,6 +111,24 @@ def _dp_worker(rank, world, port, out):
     sizes = [dp.shard_bounds(1003, r, world) for r in range(world)]
     assert sizes[0][0] == 0 and sizes[-1][1] == 1003 and all(a[1] == b[0] for a, b in zip(sizes[:-1], sizes[1:]))
     assert dp.rank_seed(7) == 7 + rank
+    # sharded exchange: reduce-scatter -> per-shard update -> all-gather must equal all-reduce -> full update
+    n = 1003
+    ex = dp.ShardedExchange(n)
+    assert ex.n_padded % (world * 8) == 0 and ex.n_padded >= n and ex.hi - ex.lo == ex.shard
+    torch.manual_seed(100 + rank)
+    grad = torch.zeros(ex.n_padded)
+    grad[:n] = torch.randn(n)
+    params = torch.arange(ex.n_padded, dtype=torch.float32)          # identical on every rank
+    full = grad.clone()
+    dp.allreduce_gradient_(full)
+    want = (params - 0.1 * full).to(torch.float16)
+    g_shard = torch.zeros(ex.shard)
+    ex.reduce_scatter(grad, g_shard)
+    assert torch.allclose(g_shard, full[ex.lo:ex.hi])
+    p_shard = (params[ex.lo:ex.hi] - 0.1 * g_shard).to(torch.float16)
+    got = torch.zeros(ex.n_padded, dtype=torch.float16)
+    ex.all_gather(got, p_shard)
+    assert torch.equal(got, want)
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
