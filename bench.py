@@ -372,7 +372,9 @@ def profile_kernels(eng, pool, load, iters=5):
     for obj, name in ((E.rm, "march_rays_train"), (E.rm, "composite_rays_train_forward_ex"),
                       (E.rm, "composite_rays_train_backward_ex"), (E.ff, "ffmlp_forward")):
         saved.append((obj, name, wrap(obj, name, name)))
-    lib_names = ["lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_ffmlp_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
+    lib_names = ["lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_ray_terms", "lnb_field_forward",
+                 "lnb_field_head_backward",
+                 "lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_ffmlp_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
                  "lnb_lidar_loss", "lnb_field_head_out_grad", "lnb_ffmlp_backward_accumulate", "lnb_field_sigma_out_grad",
                  "lnb_grid_encode_backward_ex"]
 
@@ -444,8 +446,17 @@ def profile_kernels(eng, pool, load, iters=5):
                                        "per sample 512 B gathers + 12 B xyz + 64 B features out"),
         "lnb_grid_encode_backward_ex": (rows * (2 * c.num_levels * 8 * c.level_dim * 4 + 12 + 64),
                                         "per sample 16x8 fp32x2 read-modify-write (2048 B) + 12 B xyz + 64 B grad in"),
-        "lnb_ffmlp_backward_accumulate": (rows * (32 + 192 + 2 * 128 + 192 + 64 + 2 * 128 + 64) // 2,
-                                          "per sample grad in + inputs + saved activations read, grad_inputs written (avg of both MLPs)"),
+        "lnb_ffmlp_backward_accumulate": (
+            (rows * (32 + 64 + c.sigma_layers * 128 + 64), "density MLP, per sample: 32 B grad in + 64 B inputs + "
+             "saved activations read, 64 B grad_inputs written") if eng.fused else
+            (rows * (32 + 192 + 2 * 128 + 192 + 64 + 2 * 128 + 64) // 2,
+             "per sample grad in + inputs + saved activations read, grad_inputs written (avg of both MLPs)")),
+        "lnb_field_forward": (rows * (2 * eng.enc_dim + (c.sigma_layers + c.head_layers) * 128 + 32 + 4 + 8 + 4),
+                              "per sample 64 B features + 4 B ray id in; saved activations of both nets, 32 B sig_out, "
+                              "sigma, rgb out"),
+        "lnb_field_head_backward": (rows * (8 + 8 + 4 + 32 + 4 + c.head_layers * 128 + 32),
+                                    "per sample g_rgb, rgb, g_sigma, sig_out, ray id, saved head activations in; "
+                                    "32 B g_sig_out out (per-ray encodings come from L2)"),
         "lnb_ffmlp_forward_ex": (rows * ((64 + 32 + 2 * 128) + (192 + 32 + 2 * 128)) // 2,
                           "per sample inputs + outputs + 2 saved activation rows (avg of both MLPs)"),
     }

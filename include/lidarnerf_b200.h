@@ -77,6 +77,15 @@ int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
                          float *deltas, int32_t *rays, int32_t *counter, const float *noises,
                          lnb_stream_t stream);
 
+/* Extension: additionally writes ray_ids [M] (nullable) = rays_o/rays_d row each sample belongs to, and accepts
+ * dirs == NULL when ray_ids is given (all samples of a ray share its direction; the fused field kernels below look
+ * the direction terms up per ray instead of reading 12 B per sample). */
+int lnb_march_rays_train_ex(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                            uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
+                            float *deltas, int32_t *rays, int32_t *counter, const float *noises,
+                            int32_t *ray_ids, lnb_stream_t stream);
+
 /* raymarching.cu:657-678.  rgbs [M,3]; outputs indexed by rays[n,0]. */
 int lnb_composite_rays_train_forward(const float *sigmas, const float *rgbs, const float *deltas,
                                      const int32_t *rays, uint32_t M, uint32_t N, float T_thresh,
@@ -248,6 +257,9 @@ int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq,
  * partially filled tile (raymarching.py:235-237 zero-fills whole buffers on the host side every call) */
 int lnb_zero_sample_tail(float *xyzs, float *dirs, float *deltas, const int32_t *counter, uint32_t M,
                          lnb_stream_t stream);
+/* same with nullable dirs and an optional ray_ids [M] tail (set to ray 0) */
+int lnb_zero_sample_tail_ex(float *xyzs, float *dirs, float *deltas, int32_t *ray_ids, const int32_t *counter,
+                            uint32_t M, lnb_stream_t stream);
 /* sigma_out [M,16] fp16 (density head output), dirs [M,3] ->
  *   sigma [M] fp32 = exp(h0) * density_scale ; head_in [M,in_pad] fp16 = [freq_enc(dir,degree) | geo_feat(15) | 0] */
 int lnb_field_head_input(const void *sigma_out, const float *dirs, uint32_t M, uint32_t degree, uint32_t in_pad,
@@ -269,6 +281,37 @@ int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const 
 /* get_lidar_rays (dataset/base_dataset.py:85-100): pose [3x4 or 4x4 row-major], inds [N] flat pixel ids */
 int lnb_lidar_rays(const float *pose, const int32_t *inds, uint32_t N, uint32_t H, uint32_t W, float fov_up,
                    float fov, float *rays_o, float *rays_d, lnb_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Fused LiDAR field network (density MLP -> LiDAR head) - same arithmetic as
+ *   lnb_ffmlp_forward_ex(sigma) -> lnb_field_head_input -> lnb_ffmlp_forward_ex(head) -> lnb_field_head_rgb
+ * (nerf/network.py:162-237 wiring over ffmlp.cu:460-576 / freqencoder.cu:34-61), using the fact that every sample
+ * of a ray shares its direction: W_in[:, :nfreq] . freq_enc(dir) is evaluated once per ray (lnb_field_ray_terms)
+ * and enters the head's first layer as a per-ray bias; only the 15 geo features go through the tensor cores.
+ * Layer shapes as lnb_ffmlp_*: hidden = 64, outputs padded to 16, ReLU, no biases.
+ * ---------------------------------------------------------------------------------------- */
+/* LNB_OK when the fused kernels implement this configuration (else use the unfused chain) */
+int lnb_field_supported(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                        uint32_t degree, uint32_t hidden);
+/* rays_d [N,3], w_head = flat fp16 head weights ->
+ *   ray_enc [N,in_pad] fp16 = [freq_enc(dir) | 0] ; ray_bias [N,64] fp32 = W_in[:, :nfreq] . ray_enc[n, :nfreq] */
+int lnb_field_ray_terms(const float *rays_d, const void *w_head, uint32_t N, uint32_t degree, uint32_t in_pad,
+                        void *ray_enc, float *ray_bias, lnb_stream_t stream);
+/* enc [M,enc_dim] fp16 -> sigma [M] fp32 = exp(h0)*density_scale, rgb [M,2] fp32 = sigmoid(head[0:2]); keeps for the
+ * backward pass: fb_sigma [sigma_layers,M,64], sig_out [M,16], fb_head [head_layers,M,64] (all fp16). */
+int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, const int32_t *ray_ids,
+                      const float *ray_bias, uint32_t M, uint32_t enc_dim, uint32_t sigma_layers,
+                      uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                      float density_scale, void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                      const int32_t *n_active, lnb_stream_t stream);
+/* LiDAR-head backward = lnb_field_head_out_grad + lnb_ffmlp_backward_accumulate(head) + lnb_field_sigma_out_grad:
+ * g_rgb/rgb [M,2], g_sigma [M] -> g_sig_out [M,16] fp16 (gradient w.r.t. the density MLP's output row) and
+ * grad_w_head_f32 (+=, flat fp32, head weight layout). */
+int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                            const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                            uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                            float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
+                            lnb_stream_t stream);
 
 #ifdef __cplusplus
 }

@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "liblnb200.so")
+LIB_PATH = os.environ.get("LNB200_LIB") or os.path.join(_HERE, "lib", "liblnb200.so")   # override: diagnostic builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -38,6 +38,8 @@ SYMBOLS = [
     "lnb_ffmlp_forward", "lnb_ffmlp_inference", "lnb_ffmlp_backward_workspace_bytes", "lnb_ffmlp_backward",
     "lnb_allocate_splitk", "lnb_free_splitk", "lnb_adam_step",
     "lnb_grid_encode_forward_ex", "lnb_grid_encode_backward_ex", "lnb_ffmlp_backward_accumulate", "lnb_ffmlp_forward_ex",
+    "lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_supported", "lnb_field_ray_terms",
+    "lnb_field_forward", "lnb_field_head_backward",
     "lnb_zero_sample_tail", "lnb_field_head_input", "lnb_field_head_rgb", "lnb_lidar_loss",
     "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays",
 ]

@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIB_DIR, "liblnb200.so")
-UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "optim", "fused"]
+UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "field", "optim", "fused"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -35,8 +35,13 @@ def _newest_header():
     return max(os.path.getmtime(h) for h in hs)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, trace=False):
+    """trace=True builds the diagnostic variant lib/liblnb200_trace.so (-DLNB_TRACE: in-kernel timelines of the MLP
+    backward, read by scripts/diag_bwd_trace.py); the shipped library never contains that code."""
+    global OBJ_DIR, LIB
     nvcc = _nvcc()
+    if trace:
+        OBJ_DIR, LIB = os.path.join(HERE, "build_trace"), os.path.join(LIB_DIR, "liblnb200_trace.so")
     os.makedirs(LIB_DIR, exist_ok=True)
     os.makedirs(OBJ_DIR, exist_ok=True)
     hdr = _newest_header()
@@ -49,7 +54,7 @@ def build(force=False, verbose=False):
 
     def compile_one(item):
         u, src, obj = item
-        cmd = [nvcc, *ARCH, *FLAGS, "-c", src, "-o", obj]
+        cmd = [nvcc, *ARCH, *FLAGS, *(["-DLNB_TRACE"] if trace else []), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -72,4 +77,4 @@ def build(force=False, verbose=False):
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

@@ -1,0 +1,425 @@
+// LiDAR field network as two fused tensor-core kernels: density MLP -> LiDAR head in one forward kernel, and the
+// LiDAR-head backward with its glue folded in.  Same arithmetic as the unfused chain
+//   ffmlp(sigma) -> [trunc_exp | concat(freq_enc(dir), geo_feat)] -> ffmlp(head) -> sigmoid
+// (nerf/network.py:162-237 wiring, ffmlp.cu / freqencoder.cu kernels of the reference), restructured around one fact:
+// every sample of a ray has the SAME direction.  The head's first layer is split as
+//   W_in . [enc(dir) | geo | 0]  =  W_in[:, :nfreq] . enc(dir_ray)   (a per-ray 64-vector, computed once per ray)
+//                                 + W_in[:, nfreq:nfreq+15] . geo     (a K=16..32 tensor-core step per sample)
+// so the [M, 96] fp16 head input is never materialised: the head reads the density MLP's 16 outputs straight out of
+// tensor memory, and the backward gathers the per-ray encoding rows (L2-resident, N x 96 fp16) for dW_in.
+//
+// What this removes from the step (per sample): 192 B head_in write + 192 B read (fwd) + 192 B read (bwd),
+// 192 B g_head_in write + 30 B read, 32 B head_out, 32 B g_head_out, and five launches.
+#include "common.cuh"
+#include "mlp_tiles.cuh"
+#include "mlp_bwd.cuh"
+
+namespace lnb {
+namespace {
+
+struct FieldShape {
+    Shape s;             // density MLP (input = hash-grid features)
+    Shape h;             // LiDAR head (input = [enc(dir) | geo | pad], in_dim = in_pad)
+    uint32_t nfreq;      // 3 + 6 * degree: first geo column of the head input
+    uint32_t geo_tile;   // nfreq / 64   (64-column tile of W_in that holds the geo columns)
+    uint32_t geo_off;    // nfreq % 64
+};
+
+// -----------------------------------------------------------------------------------------------------
+// per-ray direction terms:  ray_enc[n] = fp16([freq_enc(dir_n) | 0...])  (freqencoder.cu:34-61 layout),
+//                           ray_bias[n][h] = sum_{j<nfreq} W_in[h][j] * ray_enc[n][j]   (fp32)
+// -----------------------------------------------------------------------------------------------------
+constexpr uint32_t kRaysPerBlock = 16;   // 4 rays at a time (one per 64-thread group), 4 rounds
+__global__ void __launch_bounds__(256)
+k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_head, uint32_t N, uint32_t deg,
+                uint32_t in_pad, __half *__restrict__ ray_enc, float *__restrict__ ray_bias) {
+    // the first-layer weights are staged once per block (row pitch in_pad + 2 halves: odd word stride, no bank
+    // conflicts when thread h walks row h) and reused for kRaysPerBlock rays
+    __shared__ __align__(16) __half w[kHid * (128 + 2)];
+    __shared__ float e[4][128];
+    const uint32_t nfreq = 3 + 6 * deg;
+    const uint32_t pitch = in_pad + 2;
+    for (uint32_t q = threadIdx.x; q < kHid * in_pad / 2; q += 256) {       // in_pad is even: copy half2 words
+        const uint32_t r = (2 * q) / in_pad, c = 2 * q - r * in_pad;
+        *reinterpret_cast<__half2 *>(w + r * pitch + c) = reinterpret_cast<const __half2 *>(w_head)[q];
+    }
+    const float half_pi = 3.141592653589793f / 2;
+    const uint32_t sub = threadIdx.x >> 6, h = threadIdx.x & 63u;
+    for (uint32_t round = 0; round < kRaysPerBlock / 4; ++round) {
+        const uint32_t n = blockIdx.x * kRaysPerBlock + round * 4 + sub;
+        const bool live = n < N;
+        float d[3] = {0.f, 0.f, 0.f};
+        if (live) d[0] = rays_d[n * 3], d[1] = rays_d[n * 3 + 1], d[2] = rays_d[n * 3 + 2];
+        __syncthreads();   // weights staged (first round) / previous round's e[] fully consumed
+        if (live)
+            for (uint32_t j = h; j < in_pad; j += 64) {
+                float v = 0.f;
+                if (j < 3) {
+                    v = d[j];
+                } else if (j < nfreq) {
+                    const uint32_t f = (j - 3) / 6, r = (j - 3) % 6, a = r % 3;
+                    const float arg = scalbnf(d[a], (int)f);
+                    v = __sinf(arg + (r >= 3 ? 1.f : 0.f) * half_pi);
+                }
+                const __half hv = __float2half_rn(v);
+                ray_enc[(size_t)n * in_pad + j] = hv;
+                e[sub][j] = __half2float(hv);
+            }
+        __syncthreads();
+        if (live) {
+            const __half *wr = w + h * pitch;
+            float acc = 0.f;
+            for (uint32_t j = 0; j < nfreq; ++j) acc = fmaf(__half2float(wr[j]), e[sub][j], acc);
+            ray_bias[(size_t)n * kHid + h] = acc;
+        }
+    }
+}
+
+// accumulator (64 fp32 columns of this thread's row) -> (+bias) -> ReLU -> fp16 -> operand tile row
+__device__ __forceinline__ void epilogue_relu(uint32_t d_hid, uint32_t lane_sel, uint32_t s_h, uint32_t row,
+                                              const float4 *__restrict__ bias) {
+#pragma unroll
+    for (uint32_t half_id = 0; half_id < 2; ++half_id) {
+        uint32_t v[32];
+        tmem_ld32(d_hid + lane_sel + half_id * 32, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (uint32_t c = 0; c < 4; ++c) {
+            float f[8];
+#pragma unroll
+            for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]);
+            if (bias) {
+                const float4 b0 = __ldg(bias + half_id * 8 + c * 2), b1 = __ldg(bias + half_id * 8 + c * 2 + 1);
+                f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+                f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+            }
+            uint4 pk;
+            pk.x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
+            pk.y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
+            pk.z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
+            pk.w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
+            sts128(tile_chunk_addr(s_h, row, half_id * 4 + c), pk);
+        }
+    }
+}
+
+// =====================================================================================================
+// forward: enc [M, enc_dim] -> sigma [M], rgb [M,2]  (+ saved activations of both nets and sig_out for backward)
+// =====================================================================================================
+__global__ void __launch_bounds__(kThreads)
+k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const __half *__restrict__ Wh,
+            const int32_t *__restrict__ ray_ids, const float *__restrict__ ray_bias, uint32_t B, FieldShape fs,
+            float density_scale, __half *__restrict__ fb_s, __half *__restrict__ sig_out, float *__restrict__ sigma,
+            __half *__restrict__ fb_h, float *__restrict__ rgb, const int32_t *__restrict__ n_active) {
+    extern __shared__ uint8_t smem_raw[];
+    const Shape &ss = fs.s;
+    const Shape &sh = fs.h;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    const uint32_t s_ws_in = sbase;
+    const uint32_t s_ws_hid = s_ws_in + ss.kt_in * kWTileBytes;
+    const uint32_t s_ws_out = s_ws_hid + ss.n_hid * kWTileBytes;
+    const uint32_t s_wh_geo = s_ws_out + 2048;
+    const uint32_t s_wh_hid = s_wh_geo + kWTileBytes;
+    const uint32_t s_wh_out = s_wh_hid + sh.n_hid * kWTileBytes;
+    const uint32_t s_x = s_wh_out + 2048;
+    const uint32_t s_h = s_x + ss.kt_in * kTileBytes;
+    const uint32_t s_bar = s_h + kTileBytes;
+    const uint32_t s_slot = s_bar + 8;
+
+    const uint32_t warp = threadIdx.x >> 5;
+    const uint32_t row = threadIdx.x;
+
+    if (warp == 0) tmem_alloc(s_slot, 128);
+    if (threadIdx.x == 32) {
+        mbar_init(s_bar, 1);
+        mbar_init_fence();
+    }
+    load_tiles(s_ws_in, kWTileBytes, Ws, kHid, ss.in_dim, ss.in_dim, true);
+    for (uint32_t l = 0; l < ss.n_hid; ++l)
+        load_tiles(s_ws_hid + l * kWTileBytes, kWTileBytes, Ws + ss.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
+                   kHid, false);
+    load_tiles(s_ws_out, kWOutBytes, Ws + ss.w_in_elems + (size_t)ss.n_hid * kHid * kHid, kOut, kHid, kHid, false);
+    // head: only the 64-column tile of W_in that holds the geo columns (the enc(dir) columns act through ray_bias)
+    load_tiles(s_wh_geo, kWTileBytes, Wh + fs.geo_tile * 64, kHid, min(64u, sh.in_dim - fs.geo_tile * 64), sh.in_dim,
+               true);
+    for (uint32_t l = 0; l < sh.n_hid; ++l)
+        load_tiles(s_wh_hid + l * kWTileBytes, kWTileBytes, Wh + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
+                   kHid, false);
+    load_tiles(s_wh_out, kWOutBytes, Wh + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid, false);
+    cp_async_wait_all();
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = lds32(s_slot);
+    const uint32_t d_hid = tmem;
+    const uint32_t d_out = tmem + 64;
+    const uint32_t lane_sel = (warp * 32u) << 16;
+    const uint32_t ks_geo = (fs.geo_off + 15 + 15) / 16;     // K steps covering the geo columns inside their tile
+
+    uint32_t phase = 0;
+    const uint32_t n_tiles = active_rows(B, n_active) / kRows;
+    if (blockIdx.x < n_tiles)
+        load_tiles(s_x, kTileBytes, X + (size_t)blockIdx.x * kRows * ss.in_dim, kRows, ss.in_dim, ss.in_dim, false);
+    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const size_t row0 = (size_t)tile * kRows;
+        const uint32_t rid = (uint32_t)ray_ids[row0 + row];
+        cp_async_wait_all();
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {   // warp-collective MMA issue (one elected lane)
+            fence_after_sync();
+            for (uint32_t t = 0; t < ss.kt_in; ++t) {
+                const uint32_t cols = min(64u, ss.in_dim - t * 64);
+                issue_kmajor(d_hid, s_x + t * kTileBytes, s_ws_in + t * kWTileBytes, cols / 16, kIdescFwdHid, t > 0);
+            }
+            mma_commit_elect(s_bar);
+        }
+
+        // ---------------- density MLP ----------------
+        for (uint32_t layer = 0; layer <= ss.n_hid; ++layer) {
+            mbar_wait(s_bar, phase);
+            phase ^= 1;
+            fence_after_sync();
+            if (layer == 0 && tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's features
+                load_tiles(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * ss.in_dim, kRows, ss.in_dim,
+                           ss.in_dim, false);
+            epilogue_relu(d_hid, lane_sel, s_h, row, nullptr);
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (warp == 0) {
+                fence_after_sync();
+                if (layer < ss.n_hid)
+                    issue_kmajor(d_hid, s_h, s_ws_hid + layer * kWTileBytes, 4, kIdescFwdHid, false);
+                else
+                    issue_kmajor(d_out, s_h, s_ws_out, 4, kIdescFwdOut, false);
+                mma_commit_elect(s_bar);
+            }
+            store_tile_rows(s_h, fb_s + ((size_t)layer * B + row0) * kHid);
+            __syncthreads();
+        }
+
+        // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand tile
+        mbar_wait(s_bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        {
+            uint32_t v[16];
+            tmem_ld16(d_out + lane_sel, v);
+            tmem_ld_wait();
+            __half hv[16];
+#pragma unroll
+            for (uint32_t k = 0; k < 16; ++k) hv[k] = __float2half_rn(__uint_as_float(v[k]));
+            uint4 lo, hi;
+            const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
+            lo = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+            hi = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+            uint4 *dst = reinterpret_cast<uint4 *>(sig_out + (row0 + row) * kOut);
+            dst[0] = lo;
+            dst[1] = hi;
+            sigma[row0 + row] = __expf(__half2float(hv[0])) * density_scale;    // activation.py:6-20 (forward)
+            // head operand: zeros over the K range, geo_feat = sig_out[1..15] at columns geo_off .. geo_off+14
+            for (uint32_t c = 0; c < 2 * ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
+#pragma unroll
+            for (uint32_t k = 1; k < 16; ++k)
+                sts16(tile_elem_addr(s_h, row, fs.geo_off + k - 1), __half_as_ushort(hv[k]));
+        }
+        fence_proxy_async();
+        fence_before_sync();
+        __syncthreads();
+        if (warp == 0) {   // warp-collective MMA issue (one elected lane)
+            fence_after_sync();
+            issue_kmajor(d_hid, s_h, s_wh_geo, ks_geo, kIdescFwdHid, false);
+            mma_commit_elect(s_bar);
+        }
+
+        // ---------------- LiDAR head ----------------
+        const float4 *bias = reinterpret_cast<const float4 *>(ray_bias + (size_t)rid * kHid);
+        for (uint32_t layer = 0; layer <= sh.n_hid; ++layer) {
+            mbar_wait(s_bar, phase);
+            phase ^= 1;
+            fence_after_sync();
+            epilogue_relu(d_hid, lane_sel, s_h, row, layer == 0 ? bias : nullptr);
+            fence_proxy_async();
+            fence_before_sync();
+            __syncthreads();
+            if (warp == 0) {
+                fence_after_sync();
+                if (layer < sh.n_hid)
+                    issue_kmajor(d_hid, s_h, s_wh_hid + layer * kWTileBytes, 4, kIdescFwdHid, false);
+                else
+                    issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
+                mma_commit_elect(s_bar);
+            }
+            store_tile_rows(s_h, fb_h + ((size_t)layer * B + row0) * kHid);
+            __syncthreads();
+        }
+
+        // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
+        mbar_wait(s_bar, phase);
+        phase ^= 1;
+        fence_after_sync();
+        {
+            uint32_t v[16];
+            tmem_ld16(d_out + lane_sel, v);
+            tmem_ld_wait();
+            const float a = __half2float(__float2half_rn(__uint_as_float(v[0])));
+            const float b = __half2float(__float2half_rn(__uint_as_float(v[1])));
+            reinterpret_cast<float2 *>(rgb)[row0 + row] = make_float2(1.f / (1.f + __expf(-a)), 1.f / (1.f + __expf(-b)));
+        }
+        fence_before_sync();
+    }
+
+    __syncthreads();
+    if (warp == 0) tmem_dealloc(tmem, 128);
+}
+
+int make_shape(uint32_t in_dim, uint32_t nl, Shape *sh) {
+    if (in_dim == 0 || in_dim % 16 != 0 || in_dim > 128 || nl < 2) return LNB_ERR_UNSUPPORTED;
+    sh->in_dim = in_dim;
+    sh->kt_in = (in_dim + 63) / 64;
+    sh->n_hid = nl - 1;
+    sh->w_in_elems = kHid * in_dim;
+    return LNB_OK;
+}
+
+int make_field_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                     uint32_t degree, uint32_t hidden, FieldShape *fs) {
+    if (hidden != kHid) return LNB_ERR_UNSUPPORTED;
+    int rc = make_shape(enc_dim, sigma_layers, &fs->s);
+    if (rc != LNB_OK) return rc;
+    rc = make_shape(head_in_pad, head_layers, &fs->h);
+    if (rc != LNB_OK) return rc;
+    fs->nfreq = 3 + 6 * degree;
+    if (fs->nfreq + 15 > head_in_pad) return LNB_ERR_INVALID_ARGUMENT;
+    fs->geo_tile = fs->nfreq / 64;
+    fs->geo_off = fs->nfreq % 64;
+    if (fs->geo_off + 15 > 64) return LNB_ERR_UNSUPPORTED;      // geo columns must sit inside one 64-column tile
+    return LNB_OK;
+}
+
+int sm_count_field() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+}  // namespace lnb
+
+using namespace lnb;
+
+extern "C" {
+
+int lnb_field_supported(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                        uint32_t degree, uint32_t hidden) {
+    FieldShape fs;
+    int rc = make_field_shape(enc_dim, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
+    if (rc != LNB_OK) return rc;
+    if (!(fs.geo_off % 32 + 15 <= 32 && (fs.geo_off == 11 || fs.geo_off == 39))) return LNB_ERR_UNSUPPORTED;
+    return LNB_OK;
+}
+
+int lnb_field_ray_terms(const float *rays_d, const void *w_head, uint32_t N, uint32_t degree, uint32_t in_pad,
+                        void *ray_enc, float *ray_bias, lnb_stream_t stream) {
+    if (!rays_d || !w_head || !ray_enc || !ray_bias) return LNB_ERR_INVALID_ARGUMENT;
+    if (in_pad > 128 || in_pad % 8 != 0 || 3 + 6 * degree + 15 > in_pad) return LNB_ERR_INVALID_ARGUMENT;
+    if (N == 0) return LNB_OK;
+    k_ray_dir_terms<<<(N + kRaysPerBlock - 1) / kRaysPerBlock, 256, 0, as_stream(stream)>>>(rays_d, static_cast<const __half *>(w_head), N, degree, in_pad,
+                                                      static_cast<__half *>(ray_enc), ray_bias);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, const int32_t *ray_ids,
+                      const float *ray_bias, uint32_t M, uint32_t enc_dim, uint32_t sigma_layers,
+                      uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                      float density_scale, void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                      const int32_t *n_active, lnb_stream_t stream) {
+    if (!enc || !w_sigma || !w_head || !ray_ids || !ray_bias || !fb_sigma || !sig_out || !sigma || !fb_head || !rgb)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (M % kRows != 0) return LNB_ERR_INVALID_ARGUMENT;
+    FieldShape fs;
+    int rc = make_field_shape(enc_dim, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
+    if (rc != LNB_OK) return rc;
+    if (M == 0) return LNB_OK;
+    const size_t smem = 1024 + (size_t)(fs.s.kt_in + fs.s.n_hid + 1 + fs.h.n_hid) * kWTileBytes + 2 * 2048 +
+                        (size_t)(fs.s.kt_in + 1) * kTileBytes + 64;
+    if (smem > 220 * 1024) return LNB_ERR_UNSUPPORTED;
+    cudaError_t e = cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    const uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
+    const uint32_t cap = (uint32_t)sm_count_field() * (per_sm < 1 ? 1u : (per_sm > 4 ? 4u : per_sm));
+    const uint32_t tiles = M / kRows;
+    k_field_fwd<<<tiles < cap ? tiles : cap, kThreads, smem, as_stream(stream)>>>(
+        static_cast<const __half *>(enc), static_cast<const __half *>(w_sigma), static_cast<const __half *>(w_head),
+        ray_ids, ray_bias, M, fs, density_scale, static_cast<__half *>(fb_sigma), static_cast<__half *>(sig_out), sigma,
+        static_cast<__half *>(fb_head), rgb, n_active);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                            const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                            uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                            float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
+                            lnb_stream_t stream) {
+    if (!g_rgb || !rgb || !g_sigma || !sig_out || !ray_ids || !ray_enc || !w_head || !fb_head || !g_sig_out ||
+        !grad_w_head_f32)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (M % kRows != 0) return LNB_ERR_INVALID_ARGUMENT;
+    FieldShape fs;
+    int rc = make_field_shape(32, 2, head_in_pad, head_layers, degree, hidden, &fs);
+    if (rc != LNB_OK) return rc;
+    if (M == 0) return LNB_OK;
+    BwdArgs a = {};
+    a.W = static_cast<const __half *>(w_head);
+    a.fbuf = static_cast<const __half *>(fb_head);
+    a.B = M;
+    a.sh = fs.h;
+    a.wgrad = grad_w_head_f32;
+    a.n_active = n_active;
+    a.g_rgb = g_rgb;
+    a.rgb = rgb;
+    a.g_sigma = g_sigma;
+    a.sig_out = static_cast<const __half *>(sig_out);
+    a.ray_ids = ray_ids;
+    a.ray_enc = static_cast<const __half *>(ray_enc);
+    a.g_sig_out = static_cast<__half *>(g_sig_out);
+    a.density_scale = density_scale;
+    a.nfreq = fs.nfreq;
+    a.geo_tile = fs.geo_tile;
+    int rc2;
+    if (fs.geo_off == 11) rc2 = launch_mlp_bwd<true, 0, 11>(a, (uint32_t)sm_count_field(), as_stream(stream));        // degree 12
+    else if (fs.geo_off == 39) rc2 = launch_mlp_bwd<true, 32, 7>(a, (uint32_t)sm_count_field(), as_stream(stream));   // degree 6
+    else return LNB_ERR_UNSUPPORTED;
+    if (rc2 != LNB_OK) return rc2;
+    count_launch();
+    return launch_status();
+}
+
+#ifdef LNB_TRACE
+// diagnostic builds only (build.py --trace): timeline recorded by CTA 0 of the head backward kernel
+int lnb_debug_bwd_trace_head(unsigned long long *host_out, uint32_t max_events, int reset) {
+    unsigned int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_bwd_trace_n, sizeof(n));
+    if (n > 16384u) n = 16384u;
+    if (n > max_events) n = max_events;
+    if (host_out && n) cudaMemcpyFromSymbol(host_out, g_bwd_trace, sizeof(unsigned long long) * n);
+    if (reset) {
+        const unsigned int zero = 0;
+        cudaMemcpyToSymbol(g_bwd_trace_n, &zero, sizeof(zero));
+    }
+    return (int)n;
+}
+#endif
+
+}  // extern "C"

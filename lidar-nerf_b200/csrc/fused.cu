@@ -18,13 +18,14 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
 // buffers on the host side every call).
 __global__ void __launch_bounds__(kThreads)
 k_zero_tail(float *__restrict__ xyzs, float *__restrict__ dirs, float *__restrict__ deltas,
-            const int32_t *__restrict__ counter, uint32_t M) {
+            int32_t *__restrict__ ray_ids, const int32_t *__restrict__ counter, uint32_t M) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= active_rows(M, counter)) return;      // only up to the end of the last partially filled 128-row tile
     const uint32_t used = (uint32_t)max(counter[0], 0);
     if (i < used) return;
     xyzs[i * 3] = xyzs[i * 3 + 1] = xyzs[i * 3 + 2] = 0.f;
-    dirs[i * 3] = dirs[i * 3 + 1] = dirs[i * 3 + 2] = 0.f;
+    if (dirs) dirs[i * 3] = dirs[i * 3 + 1] = dirs[i * 3 + 2] = 0.f;
+    if (ray_ids) ray_ids[i] = 0;
     reinterpret_cast<float2 *>(deltas)[i] = make_float2(0.f, 0.f);
 }
 
@@ -186,13 +187,19 @@ using namespace lnb;
 
 extern "C" {
 
-int lnb_zero_sample_tail(float *xyzs, float *dirs, float *deltas, const int32_t *counter, uint32_t M,
-                         lnb_stream_t stream) {
-    if (!xyzs || !dirs || !deltas || !counter) return LNB_ERR_INVALID_ARGUMENT;
+int lnb_zero_sample_tail_ex(float *xyzs, float *dirs, float *deltas, int32_t *ray_ids, const int32_t *counter,
+                            uint32_t M, lnb_stream_t stream) {
+    if (!xyzs || !deltas || !counter) return LNB_ERR_INVALID_ARGUMENT;
     if (M == 0) return LNB_OK;
-    k_zero_tail<<<nblk(M), kThreads, 0, as_stream(stream)>>>(xyzs, dirs, deltas, counter, M);
+    k_zero_tail<<<nblk(M), kThreads, 0, as_stream(stream)>>>(xyzs, dirs, deltas, ray_ids, counter, M);
     count_launch();
     return launch_status();
+}
+
+int lnb_zero_sample_tail(float *xyzs, float *dirs, float *deltas, const int32_t *counter, uint32_t M,
+                         lnb_stream_t stream) {
+    if (!dirs) return LNB_ERR_INVALID_ARGUMENT;
+    return lnb_zero_sample_tail_ex(xyzs, dirs, deltas, nullptr, counter, M, stream);
 }
 
 int lnb_field_head_input(const void *sigma_out, const float *dirs, uint32_t M, uint32_t degree, uint32_t in_pad,

@@ -328,13 +328,18 @@ struct NoEmit {
 };
 
 struct SampleWriter {
-    float *xyzs, *dirs, *deltas;
+    float *xyzs, *dirs, *deltas;   // dirs may be null (extended entry point: the fused field kernels use ray ids)
     float dx, dy, dz;
+    int32_t *ray_ids = nullptr;    // optional [M]: index of the ray each sample belongs to
+    int32_t ray = 0;
     __device__ __forceinline__ void operator()(uint32_t rank, const Cand &c, float delta_real) const {
         float *p = xyzs + (size_t)rank * 3;
         p[0] = c.x, p[1] = c.y, p[2] = c.z;
-        float *q = dirs + (size_t)rank * 3;
-        q[0] = dx, q[1] = dy, q[2] = dz;
+        if (dirs) {
+            float *q = dirs + (size_t)rank * 3;
+            q[0] = dx, q[1] = dy, q[2] = dz;
+        }
+        if (ray_ids) ray_ids[rank] = ray;
         float2 *d = reinterpret_cast<float2 *>(deltas) + rank;
         *d = make_float2(c.dt, delta_real);
     }
@@ -347,7 +352,7 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
               uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *__restrict__ nears,
               const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs,
               float *__restrict__ deltas, int32_t *__restrict__ rays, int32_t *counter,
-              const float *__restrict__ noises) {
+              const float *__restrict__ noises, int32_t *__restrict__ ray_ids) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     const MarchConst k = make_const(grid, bound, dt_gamma, max_steps, C, H);
@@ -369,8 +374,8 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
     offset = __shfl_sync(kFullMask, offset, 0);
     if (count == 0 || offset + count > M) return;
 
-    SampleWriter w{xyzs + (size_t)offset * 3, dirs + (size_t)offset * 3, deltas + (size_t)offset * 2,
-                   r.dx, r.dy, r.dz};
+    SampleWriter w{xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
+                   deltas + (size_t)offset * 2, r.dx, r.dy, r.dz, ray_ids ? ray_ids + offset : nullptr, (int32_t)n};
     march_warp<true>(k, r, t0, far, count, w);
 }
 
@@ -677,20 +682,30 @@ int lnb_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *b
     return launch_status();
 }
 
+int lnb_march_rays_train_ex(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                            float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                            uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
+                            float *deltas, int32_t *rays, int32_t *counter, const float *noises,
+                            int32_t *ray_ids, lnb_stream_t stream) {
+    LNB_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises);
+    LNB_REQUIRE(M == 0 || (xyzs && deltas && (dirs || ray_ids)));
+    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024 && max_steps >= 1);
+    if (N == 0) return LNB_OK;
+    k_march_train<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
+        rays, counter, noises, ray_ids);
+    count_launch();
+    return launch_status();
+}
+
 int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                          float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                          uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
                          float *deltas, int32_t *rays, int32_t *counter, const float *noises,
                          lnb_stream_t stream) {
-    LNB_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises);
-    LNB_REQUIRE(M == 0 || (xyzs && dirs && deltas));
-    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024 && max_steps >= 1);
-    if (N == 0) return LNB_OK;
-    k_march_train<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
-        rays, counter, noises);
-    count_launch();
-    return launch_status();
+    LNB_REQUIRE(M == 0 || dirs);
+    return lnb_march_rays_train_ex(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs,
+                                   dirs, deltas, rays, counter, noises, nullptr, stream);
 }
 
 int lnb_composite_rays_train_forward_ex(const float *sigmas, const float *rgbs, const float *deltas,

@@ -71,6 +71,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     __trap();
 }
 
+// Same, for a warp that must stay CONVERGED (the MMA-issuing warp): the exit condition is a warp vote, so the
+// compiler sees uniform control flow and can keep descriptors in uniform registers.
+__device__ __forceinline__ void mbar_wait_warp(uint32_t bar, uint32_t parity) {
+#pragma unroll 1
+    for (uint32_t spin = 0; spin < (1u << 22); ++spin) {
+        uint32_t done = 0;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (__all_sync(0xffffffffu, done)) return;
+    }
+    __trap();
+}
+
 // 1-D bulk async copy global -> shared (the TMA engine without a tensor map; SASS UBLKCP),
 // completion reported on an mbarrier as transaction bytes.
 __device__ __forceinline__ void bulk_g2s(uint32_t dst_smem, const void *src, uint32_t bytes, uint32_t bar) {
@@ -115,6 +133,26 @@ __device__ __forceinline__ void mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// Warp-collective variants: called by ALL lanes of a converged warp with warp-uniform operands; one elected lane
+// issues.  Keeping the warp converged lets the compiler hold descriptors in uniform registers - issuing from inside
+// an `if (lane == 0)` region costs an ELECT/R2UR.BROADCAST loop per instruction (~100 cycles per MMA measured).
+__device__ __forceinline__ void mma_f16_elect(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                              uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void mma_commit_elect(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar)
         : "memory");
 }
 // Arrive on `bar` when every previously issued tcgen05.mma of this thread has completed.

@@ -59,6 +59,7 @@ class FieldConfig:
     loss_scale: float = 128.0            # static loss scale for the fp16 gradient chain (GradScaler's role)
     grid_update_interval: int = 16
     perturb: bool = True                 # jitter the march start (Trainer.train_step passes perturb=True)
+    fused_field: bool = True             # density MLP + LiDAR head as the fused field kernels (csrc/field.cu)
     seed: int = 0
 
     @property
@@ -153,6 +154,13 @@ class LidarFieldEngine:
         self.dt_min = np.float32(two_sqrt3) / np.float32(c.max_steps)
         self.dt_max = np.float32(two_sqrt3) * np.float32(1 << (c.cascade - 1)) / np.float32(c.grid_size)
 
+        # fused field kernels: per-ray direction terms instead of a per-sample [M, 96] head input
+        self.fused = bool(c.fused_field) and lib.lnb_field_supported(
+            u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+            u32(c.hidden_dim)) == 0
+        self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=torch.float16, device=dev)
+        self.ray_bias = torch.zeros(N, c.hidden_dim, **f)
+
         self.M = 0
         self._graph = None
         self._alloc_samples(sample_budget or N * 64)
@@ -168,20 +176,22 @@ class LidarFieldEngine:
         f = dict(dtype=torch.float32, device=dev)
         h = dict(dtype=torch.float16, device=dev)
         self.xyzs = torch.zeros(M, 3, **f)
-        self.dirs = torch.zeros(M, 3, **f)
+        self.dirs = torch.zeros(M, 3, **f) if not self.fused else None
+        self.ray_ids = torch.zeros(M, dtype=torch.int32, device=dev)
         self.deltas = torch.zeros(M, 2, **f)
         self.enc = torch.empty(M, self.enc_dim, **h)
         self.sig_out = torch.empty(M, 16, **h)
         self.fb_sigma = torch.empty(c.sigma_layers, M, c.hidden_dim, **h)
         self.sigma = torch.empty(M, **f)
-        self.head_in = torch.empty(M, c.head_in_dim, **h)
-        self.head_out = torch.empty(M, 16, **h)
+        if not self.fused:
+            self.head_in = torch.empty(M, c.head_in_dim, **h)
+            self.head_out = torch.empty(M, 16, **h)
+            self.g_head_out = torch.empty(M, 16, **h)
+            self.g_head_in = torch.empty(M, c.head_in_dim, **h)
         self.fb_head = torch.empty(c.head_layers, M, c.hidden_dim, **h)
         self.rgb = torch.empty(M, 2, **f)
         self.g_sigma = torch.zeros(M, **f)
         self.g_rgb = torch.zeros(M, 2, **f)
-        self.g_head_out = torch.empty(M, 16, **h)
-        self.g_head_in = torch.empty(M, c.head_in_dim, **h)
         self.g_sig_out = torch.empty(M, 16, **h)
         self.g_enc = torch.empty(M, self.enc_dim, **h)
 
@@ -203,26 +213,39 @@ class LidarFieldEngine:
         torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
         torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
 
-        rm.march_rays_train(self.rays_o, self.rays_d, self.bitfield, c.bound, c.dt_gamma, c.max_steps, N, c.cascade,
-                            c.grid_size, M, self.nears, self.fars, self.xyzs, self.dirs, self.deltas, self.rays,
-                            self.counter, self.noises)
+        _ck(lib.lnb_march_rays_train_ex(p(self.rays_o), p(self.rays_d), p(self.bitfield), f32(c.bound), f32(c.dt_gamma),
+                                        u32(c.max_steps), u32(N), u32(c.cascade), u32(c.grid_size), u32(M),
+                                        p(self.nears), p(self.fars), p(self.xyzs),
+                                        p(self.dirs) if self.dirs is not None else vp(0), p(self.deltas), p(self.rays),
+                                        p(self.counter), p(self.noises), p(self.ray_ids), s), "march_rays_train")
         # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
         na = p(self.counter)
-        _ck(lib.lnb_zero_sample_tail(p(self.xyzs), p(self.dirs), p(self.deltas), na, u32(M), s), "zero_tail")
+        _ck(lib.lnb_zero_sample_tail_ex(p(self.xyzs), p(self.dirs) if self.dirs is not None else vp(0), p(self.deltas),
+                                        p(self.ray_ids), na, u32(M), s), "zero_tail")
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
             "grid_fwd")
-        _ck(lib.lnb_ffmlp_forward_ex(p(self.enc), p(self.w_sigma_h), u32(M), u32(self.enc_dim), u32(16),
-                                     u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), p(self.fb_sigma),
-                                     p(self.sig_out), na, s), "ffmlp_fwd(sigma)")
-        _ck(lib.lnb_field_head_input(p(self.sig_out), p(self.dirs), u32(M), u32(c.freq_degree), u32(c.head_in_dim),
-                                     f32(c.density_scale), p(self.sigma), p(self.head_in), na, s), "head_input")
-        _ck(lib.lnb_ffmlp_forward_ex(p(self.head_in), p(self.w_head_h), u32(M), u32(c.head_in_dim), u32(16),
-                                     u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), p(self.fb_head),
-                                     p(self.head_out), na, s), "ffmlp_fwd(head)")
-        _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), na, s), "head_rgb")
+        if self.fused:
+            _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
+                                        u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), s), "ray_terms")
+            _ck(lib.lnb_field_forward(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
+                                      p(self.ray_bias), u32(M), u32(self.enc_dim), u32(c.sigma_layers),
+                                      u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim),
+                                      f32(c.density_scale), p(self.fb_sigma), p(self.sig_out), p(self.sigma),
+                                      p(self.fb_head), p(self.rgb), na, s), "field_forward")
+        else:
+            _ck(lib.lnb_ffmlp_forward_ex(p(self.enc), p(self.w_sigma_h), u32(M), u32(self.enc_dim), u32(16),
+                                         u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), p(self.fb_sigma),
+                                         p(self.sig_out), na, s), "ffmlp_fwd(sigma)")
+            _ck(lib.lnb_field_head_input(p(self.sig_out), p(self.dirs), u32(M), u32(c.freq_degree),
+                                         u32(c.head_in_dim), f32(c.density_scale), p(self.sigma), p(self.head_in), na,
+                                         s), "head_input")
+            _ck(lib.lnb_ffmlp_forward_ex(p(self.head_in), p(self.w_head_h), u32(M), u32(c.head_in_dim), u32(16),
+                                         u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), p(self.fb_head),
+                                         p(self.head_out), na, s), "ffmlp_fwd(head)")
+            _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), na, s), "head_rgb")
         rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2, self.ws,
                                            self.depth, self.image)
         _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N), f32(c.alpha_d),
@@ -234,14 +257,22 @@ class LidarFieldEngine:
         rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb, self.deltas,
                                             self.rays, self.ws, self.depth, self.image, M, N, c.T_thresh, 2,
                                             self.g_sigma, self.g_rgb)
-        _ck(lib.lnb_field_head_out_grad(p(self.g_rgb), p(self.rgb), u32(M), p(self.g_head_out), na, s), "head_out_grad")
-        _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_head_out), p(self.head_in), p(self.w_head_h), p(self.fb_head),
-                                              u32(M), u32(c.head_in_dim), u32(16), u32(c.hidden_dim),
-                                              u32(c.head_layers), u32(0), u32(6), i32(1), p(self.g_head_in),
-                                              p(self.g_head_w), na, s), "ffmlp_bwd(head)")
-        _ck(lib.lnb_field_sigma_out_grad(p(self.g_sigma), p(self.sig_out), p(self.g_head_in), u32(M),
-                                         u32(c.head_in_dim), u32(c.freq_degree), f32(c.density_scale),
-                                         p(self.g_sig_out), na, s), "sigma_out_grad")
+        if self.fused:
+            _ck(lib.lnb_field_head_backward(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
+                                            p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
+                                            u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+                                            u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
+                                            p(self.g_head_w), na, s), "field_head_backward")
+        else:
+            _ck(lib.lnb_field_head_out_grad(p(self.g_rgb), p(self.rgb), u32(M), p(self.g_head_out), na, s),
+                "head_out_grad")
+            _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_head_out), p(self.head_in), p(self.w_head_h),
+                                                  p(self.fb_head), u32(M), u32(c.head_in_dim), u32(16),
+                                                  u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), i32(1),
+                                                  p(self.g_head_in), p(self.g_head_w), na, s), "ffmlp_bwd(head)")
+            _ck(lib.lnb_field_sigma_out_grad(p(self.g_sigma), p(self.sig_out), p(self.g_head_in), u32(M),
+                                             u32(c.head_in_dim), u32(c.freq_degree), f32(c.density_scale),
+                                             p(self.g_sig_out), na, s), "sigma_out_grad")
         _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h), p(self.fb_sigma),
                                               u32(M), u32(self.enc_dim), u32(16), u32(c.hidden_dim),
                                               u32(c.sigma_layers), u32(0), u32(6), i32(1), p(self.g_enc),

@@ -14,6 +14,26 @@ def test_fused_step_matches_cpu_restatement():
     check_engine.compare(gpu, cpu, eng.n_table)
 
 
+def test_unfused_chain_matches_cpu_restatement_and_fused_kernels():
+    """The per-op chain (ffmlp -> head_input -> ffmlp -> glue) and the fused field kernels are the same function."""
+    from oracle import check_engine
+    eng_u, gpu_u, cpu = check_engine.run_pair(n_rays=256, device=DEV, cfg=check_engine.small_config(fused_field=False, perturb=False))
+    assert not eng_u.fused
+    check_engine.compare(gpu_u, cpu, eng_u.n_table)
+    eng_f, gpu_f, _ = check_engine.run_pair(n_rays=256, device=DEV, cfg=check_engine.small_config(fused_field=True, perturb=False))
+    assert eng_f.fused, "default configuration must take the fused field kernels"
+    np.testing.assert_array_equal(gpu_f["counts"], gpu_u["counts"])
+    np.testing.assert_allclose(gpu_f["image"], gpu_u["image"], rtol=2e-3, atol=1e-3)
+    np.testing.assert_allclose(gpu_f["depth"], gpu_u["depth"], rtol=2e-3, atol=1e-3)
+    a, b = gpu_f["grad"].astype(np.float64), gpu_u["grad"].astype(np.float64)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 2e-2
+    # per-sample ray ids written by the extended march agree with the rays table
+    rays = eng_f.rays.cpu().numpy()
+    ids = eng_f.ray_ids.cpu().numpy()
+    for n, off, cnt in rays[:64]:
+        assert (ids[off:off + cnt] == n).all()
+
+
 def test_fused_step_full_size_table_matches_cpu_restatement():
     from oracle import check_engine
     cfg = check_engine.small_config(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
