@@ -75,45 +75,56 @@ k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_h
     }
 }
 
-// accumulator (64 fp32 columns of this thread's row) -> (+bias) -> ReLU -> fp16 -> operand tile row
-__device__ __forceinline__ void epilogue_relu(uint32_t d_hid, uint32_t lane_sel, uint32_t s_h, uint32_t row,
-                                              const float4 *__restrict__ bias) {
+// this thread's 32 accumulator columns -> (+bias) -> ReLU -> fp16 (four 16-byte chunks of the operand-tile row)
+__device__ __forceinline__ void epilogue_relu(uint32_t d_mine, uint32_t half, const float4 *__restrict__ bias,
+                                              uint4 (&pk)[4]) {
+    uint32_t v[32];
+    tmem_ld32(d_mine, v);
+    tmem_ld_wait();
 #pragma unroll
-    for (uint32_t half_id = 0; half_id < 2; ++half_id) {
-        uint32_t v[32];
-        tmem_ld32(d_hid + lane_sel + half_id * 32, v);
-        tmem_ld_wait();
+    for (uint32_t c = 0; c < 4; ++c) {
+        float f[8];
 #pragma unroll
-        for (uint32_t c = 0; c < 4; ++c) {
-            float f[8];
-#pragma unroll
-            for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]);
-            if (bias) {
-                const float4 b0 = __ldg(bias + half_id * 8 + c * 2), b1 = __ldg(bias + half_id * 8 + c * 2 + 1);
-                f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-                f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
-            }
-            uint4 pk;
-            pk.x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
-            pk.y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
-            pk.z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
-            pk.w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
-            sts128(tile_chunk_addr(s_h, row, half_id * 4 + c), pk);
+        for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]);
+        if (bias) {
+            const float4 b0 = __ldg(bias + half * 8 + c * 2), b1 = __ldg(bias + half * 8 + c * 2 + 1);
+            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
         }
+        pk[c].x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
+        pk[c].y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
+        pk[c].z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
+        pk[c].w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
+    }
+}
+__device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+// swizzled 128 x 64 tile -> global rows of 128 B, fully coalesced (a warp writes 512 contiguous bytes); 256 threads
+__device__ __forceinline__ void store_tile_rows_256(uint32_t t, uint32_t tile, __half *__restrict__ dst) {
+#pragma unroll
+    for (uint32_t j = 0; j < (kRows * 8) / 256; ++j) {
+        const uint32_t q = t + j * 256;
+        *reinterpret_cast<uint4 *>(dst + (size_t)q * 8) = lds128(tile_chunk_addr(tile, q >> 3, q & 7));
     }
 }
 
 // =====================================================================================================
 // forward: enc [M, enc_dim] -> sigma [M], rgb [M,2]  (+ saved activations of both nets and sig_out for backward)
+//
+// 256 epilogue threads (two per tile row, 32 accumulator columns each) + one MMA warp.  No CTA-wide barrier in the
+// tile loop: the epilogue threads publish an operand tile with mbarrier `ready` (256 arrivals), the MMA warp answers
+// each layer with tcgen05.commit on `done`.  Three CTAs per SM keep three tiles in flight.
 // =====================================================================================================
-__global__ void __launch_bounds__(kThreads)
+constexpr uint32_t kFwdEpiThreads = 256;
+constexpr uint32_t kFwdThreads = kFwdEpiThreads + 32;
+
+__global__ void __launch_bounds__(kFwdThreads, 3)
 k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const __half *__restrict__ Wh,
             const int32_t *__restrict__ ray_ids, const float *__restrict__ ray_bias, uint32_t B, FieldShape fs,
             float density_scale, __half *__restrict__ fb_s, __half *__restrict__ sig_out, float *__restrict__ sigma,
             __half *__restrict__ fb_h, float *__restrict__ rgb, const int32_t *__restrict__ n_active) {
     extern __shared__ uint8_t smem_raw[];
-    const Shape &ss = fs.s;
-    const Shape &sh = fs.h;
+    const Shape ss = fs.s;
+    const Shape sh = fs.h;
     const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t s_ws_in = sbase;
     const uint32_t s_ws_hid = s_ws_in + ss.kt_in * kWTileBytes;
@@ -123,30 +134,44 @@ k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const _
     const uint32_t s_wh_out = s_wh_hid + sh.n_hid * kWTileBytes;
     const uint32_t s_x = s_wh_out + 2048;
     const uint32_t s_h = s_x + ss.kt_in * kTileBytes;
-    const uint32_t s_bar = s_h + kTileBytes;
-    const uint32_t s_slot = s_bar + 8;
+    const uint32_t bar_ready = s_h + kTileBytes;
+    const uint32_t bar_done = bar_ready + 8;
+    const uint32_t s_slot = bar_done + 8;
 
     const uint32_t warp = threadIdx.x >> 5;
-    const uint32_t row = threadIdx.x;
+    constexpr uint32_t kMmaWarp = kFwdEpiThreads / 32;
 
-    if (warp == 0) tmem_alloc(s_slot, 128);
-    if (threadIdx.x == 32) {
-        mbar_init(s_bar, 1);
+    // cooperative cp.async of rows x cols halves (row-major, leading dimension ld) into swizzled 64-column tiles
+    auto load = [&](uint32_t tile0, uint32_t stride, const __half *src, uint32_t rows, uint32_t cols, uint32_t ld, bool zero_pad,
+                    uint32_t t, uint32_t nthr) {
+        const uint32_t kt = (cols + 63) / 64, cpr = kt * 8;
+        for (uint32_t q = t; q < rows * cpr; q += nthr) {
+            const uint32_t r = q / cpr, c = q - r * cpr;
+            const uint32_t dst = tile_chunk_addr(tile0 + (c >> 3) * stride, r, c & 7);
+            if (c * 8 < cols) cp_async16(dst, src + (size_t)r * ld + c * 8);
+            else if (zero_pad) cp_async16(dst, src, 0);
+        }
+    };
+
+    if (warp == kMmaWarp) tmem_alloc(s_slot, 128);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_ready, kFwdEpiThreads);
+        mbar_init(bar_done, 1);
         mbar_init_fence();
     }
-    load_tiles(s_ws_in, kWTileBytes, Ws, kHid, ss.in_dim, ss.in_dim, true);
-    for (uint32_t l = 0; l < ss.n_hid; ++l)
-        load_tiles(s_ws_hid + l * kWTileBytes, kWTileBytes, Ws + ss.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
-                   kHid, false);
-    load_tiles(s_ws_out, kWOutBytes, Ws + ss.w_in_elems + (size_t)ss.n_hid * kHid * kHid, kOut, kHid, kHid, false);
-    // head: only the 64-column tile of W_in that holds the geo columns (the enc(dir) columns act through ray_bias)
-    load_tiles(s_wh_geo, kWTileBytes, Wh + fs.geo_tile * 64, kHid, min(64u, sh.in_dim - fs.geo_tile * 64), sh.in_dim,
-               true);
-    for (uint32_t l = 0; l < sh.n_hid; ++l)
-        load_tiles(s_wh_hid + l * kWTileBytes, kWTileBytes, Wh + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid,
-                   kHid, false);
-    load_tiles(s_wh_out, kWOutBytes, Wh + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid, false);
-    cp_async_wait_all();
+    {
+        const uint32_t t = threadIdx.x, n = kFwdThreads;
+        load(s_ws_in, kWTileBytes, Ws, kHid, ss.in_dim, ss.in_dim, true, t, n);
+        for (uint32_t l = 0; l < ss.n_hid; ++l)
+            load(s_ws_hid + l * kWTileBytes, kWTileBytes, Ws + ss.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid, false, t, n);
+        load(s_ws_out, kWOutBytes, Ws + ss.w_in_elems + (size_t)ss.n_hid * kHid * kHid, kOut, kHid, kHid, false, t, n);
+        // head: only the 64-column tile of W_in that holds the geo columns (the enc(dir) columns act through ray_bias)
+        load(s_wh_geo, kWTileBytes, Wh + fs.geo_tile * 64, kHid, min(64u, sh.in_dim - fs.geo_tile * 64), sh.in_dim, true, t, n);
+        for (uint32_t l = 0; l < sh.n_hid; ++l)
+            load(s_wh_hid + l * kWTileBytes, kWTileBytes, Wh + sh.w_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid, false, t, n);
+        load(s_wh_out, kWOutBytes, Wh + sh.w_in_elems + (size_t)sh.n_hid * kHid * kHid, kOut, kHid, kHid, false, t, n);
+        cp_async_wait_all();
+    }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
@@ -154,126 +179,139 @@ k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const _
     const uint32_t tmem = lds32(s_slot);
     const uint32_t d_hid = tmem;
     const uint32_t d_out = tmem + 64;
-    const uint32_t lane_sel = (warp * 32u) << 16;
     const uint32_t ks_geo = (fs.geo_off + 15 + 15) / 16;     // K steps covering the geo columns inside their tile
-
-    uint32_t phase = 0;
     const uint32_t n_tiles = active_rows(B, n_active) / kRows;
-    if (blockIdx.x < n_tiles)
-        load_tiles(s_x, kTileBytes, X + (size_t)blockIdx.x * kRows * ss.in_dim, kRows, ss.in_dim, ss.in_dim, false);
-    for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const size_t row0 = (size_t)tile * kRows;
-        const uint32_t rid = (uint32_t)ray_ids[row0 + row];
-        cp_async_wait_all();
-        fence_proxy_async();
-        fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {   // warp-collective MMA issue (one elected lane)
-            fence_after_sync();
-            for (uint32_t t = 0; t < ss.kt_in; ++t) {
-                const uint32_t cols = min(64u, ss.in_dim - t * 64);
-                issue_kmajor(d_hid, s_x + t * kTileBytes, s_ws_in + t * kWTileBytes, cols / 16, kIdescFwdHid, t > 0);
-            }
-            mma_commit_elect(s_bar);
-        }
 
-        // ---------------- density MLP ----------------
-        for (uint32_t layer = 0; layer <= ss.n_hid; ++layer) {
-            mbar_wait(s_bar, phase);
-            phase ^= 1;
-            fence_after_sync();
-            if (layer == 0 && tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's features
-                load_tiles(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * ss.in_dim, kRows, ss.in_dim,
-                           ss.in_dim, false);
-            epilogue_relu(d_hid, lane_sel, s_h, row, nullptr);
-            fence_proxy_async();
-            fence_before_sync();
-            __syncthreads();
-            if (warp == 0) {
+    if (warp == kMmaWarp) {
+        // ================= MMA warp (converged; one elected lane issues) =================
+        uint32_t par = 0;
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            // density MLP: input layer, hidden layers, output layer; then the head's geo step, hidden layers, output
+            for (uint32_t step = 0; step < ss.n_hid + 2 + sh.n_hid + 2; ++step) {
+                mbar_wait_warp(bar_ready, par);
+                par ^= 1;
                 fence_after_sync();
-                if (layer < ss.n_hid)
-                    issue_kmajor(d_hid, s_h, s_ws_hid + layer * kWTileBytes, 4, kIdescFwdHid, false);
-                else
+                if (step == 0) {
+                    for (uint32_t t = 0; t < ss.kt_in; ++t) {
+                        const uint32_t cols = min(64u, ss.in_dim - t * 64);
+                        issue_kmajor(d_hid, s_x + t * kTileBytes, s_ws_in + t * kWTileBytes, cols / 16, kIdescFwdHid, t > 0);
+                    }
+                } else if (step <= ss.n_hid) {
+                    issue_kmajor(d_hid, s_h, s_ws_hid + (step - 1) * kWTileBytes, 4, kIdescFwdHid, false);
+                } else if (step == ss.n_hid + 1) {
                     issue_kmajor(d_out, s_h, s_ws_out, 4, kIdescFwdOut, false);
-                mma_commit_elect(s_bar);
+                } else if (step == ss.n_hid + 2) {
+                    issue_kmajor(d_hid, s_h, s_wh_geo, ks_geo, kIdescFwdHid, false);
+                } else if (step <= ss.n_hid + 2 + sh.n_hid) {
+                    issue_kmajor(d_hid, s_h, s_wh_hid + (step - ss.n_hid - 3) * kWTileBytes, 4, kIdescFwdHid, false);
+                } else {
+                    issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
+                }
+                mma_commit_elect(bar_done);
             }
-            store_tile_rows(s_h, fb_s + ((size_t)layer * B + row0) * kHid);
-            __syncthreads();
         }
-
-        // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand tile
-        mbar_wait(s_bar, phase);
-        phase ^= 1;
-        fence_after_sync();
-        {
-            uint32_t v[16];
-            tmem_ld16(d_out + lane_sel, v);
-            tmem_ld_wait();
-            __half hv[16];
-#pragma unroll
-            for (uint32_t k = 0; k < 16; ++k) hv[k] = __float2half_rn(__uint_as_float(v[k]));
-            uint4 lo, hi;
-            const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
-            lo = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-            hi = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-            uint4 *dst = reinterpret_cast<uint4 *>(sig_out + (row0 + row) * kOut);
-            dst[0] = lo;
-            dst[1] = hi;
-            sigma[row0 + row] = __expf(__half2float(hv[0])) * density_scale;    // activation.py:6-20 (forward)
-            // head operand: zeros over the K range, geo_feat = sig_out[1..15] at columns geo_off .. geo_off+14
-            for (uint32_t c = 0; c < 2 * ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
-#pragma unroll
-            for (uint32_t k = 1; k < 16; ++k)
-                sts16(tile_elem_addr(s_h, row, fs.geo_off + k - 1), __half_as_ushort(hv[k]));
-        }
-        fence_proxy_async();
-        fence_before_sync();
-        __syncthreads();
-        if (warp == 0) {   // warp-collective MMA issue (one elected lane)
-            fence_after_sync();
-            issue_kmajor(d_hid, s_h, s_wh_geo, ks_geo, kIdescFwdHid, false);
-            mma_commit_elect(s_bar);
-        }
-
-        // ---------------- LiDAR head ----------------
-        const float4 *bias = reinterpret_cast<const float4 *>(ray_bias + (size_t)rid * kHid);
-        for (uint32_t layer = 0; layer <= sh.n_hid; ++layer) {
-            mbar_wait(s_bar, phase);
-            phase ^= 1;
-            fence_after_sync();
-            epilogue_relu(d_hid, lane_sel, s_h, row, layer == 0 ? bias : nullptr);
+    } else {
+        // ================= epilogue threads: thread = (row, column half) =================
+        const uint32_t row = threadIdx.x & 127u;
+        const uint32_t half = (warp >> 2) & 1u;
+        const uint32_t t256 = threadIdx.x;
+        const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
+        const uint32_t d_mine = d_hid + lane_sel + 32 * half;
+        uint32_t par = 0;
+        if (blockIdx.x < n_tiles)
+            load(s_x, kTileBytes, X + (size_t)blockIdx.x * kRows * ss.in_dim, kRows, ss.in_dim, ss.in_dim, false, t256, kFwdEpiThreads);
+        for (uint32_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+            const size_t row0 = (size_t)tile * kRows;
+            const size_t r = row0 + row;
+            const uint32_t rid = (uint32_t)__ldg(ray_ids + r);
+            cp_async_wait_all();
             fence_proxy_async();
             fence_before_sync();
-            __syncthreads();
-            if (warp == 0) {
-                fence_after_sync();
-                if (layer < sh.n_hid)
-                    issue_kmajor(d_hid, s_h, s_wh_hid + layer * kWTileBytes, 4, kIdescFwdHid, false);
-                else
-                    issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
-                mma_commit_elect(s_bar);
-            }
-            store_tile_rows(s_h, fb_h + ((size_t)layer * B + row0) * kHid);
-            __syncthreads();
-        }
+            mbar_arrive(bar_ready);                       // this thread's share of the feature tile is in place
 
-        // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
-        mbar_wait(s_bar, phase);
-        phase ^= 1;
-        fence_after_sync();
-        {
-            uint32_t v[16];
-            tmem_ld16(d_out + lane_sel, v);
-            tmem_ld_wait();
-            const float a = __half2float(__float2half_rn(__uint_as_float(v[0])));
-            const float b = __half2float(__float2half_rn(__uint_as_float(v[1])));
-            reinterpret_cast<float2 *>(rgb)[row0 + row] = make_float2(1.f / (1.f + __expf(-a)), 1.f / (1.f + __expf(-b)));
+            // ---------------- density MLP ----------------
+            for (uint32_t layer = 0; layer <= ss.n_hid; ++layer) {
+                mbar_wait(bar_done, par);
+                par ^= 1;
+                fence_after_sync();
+                if (layer == 0 && tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's features
+                    load(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * ss.in_dim, kRows, ss.in_dim, ss.in_dim, false,
+                         t256, kFwdEpiThreads);
+                uint4 pk[4];
+                epilogue_relu(d_mine, half, nullptr, pk);
+                epi_sync();                                   // the previous layer's tile has been streamed out
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) sts128(tile_chunk_addr(s_h, row, half * 4 + c), pk[c]);
+                fence_proxy_async();
+                fence_before_sync();
+                mbar_arrive(bar_ready);
+                epi_sync();                                   // every row of the tile is in shared memory
+                store_tile_rows_256(t256, s_h, fb_s + ((size_t)layer * B + row0) * kHid);   // while the tensor core works
+            }
+
+            // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand tile
+            mbar_wait(bar_done, par);
+            par ^= 1;
+            fence_after_sync();
+            epi_sync();                                       // last hidden tile streamed out before s_h is reused
+            if (half == 0) {
+                uint32_t v[16];
+                tmem_ld16(d_out + lane_sel, v);
+                tmem_ld_wait();
+                __half hv[16];
+#pragma unroll
+                for (uint32_t k = 0; k < 16; ++k) hv[k] = __float2half_rn(__uint_as_float(v[k]));
+                const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
+                uint4 *dst = reinterpret_cast<uint4 *>(sig_out + r * kOut);
+                dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+                sigma[r] = __expf(__half2float(hv[0])) * density_scale;    // activation.py:6-20 (forward)
+                // head operand: zeros over the K range, geo_feat = sig_out[1..15] at columns geo_off .. geo_off+14
+                for (uint32_t c = 0; c < 2 * ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
+#pragma unroll
+                for (uint32_t k = 1; k < 16; ++k)
+                    sts16(tile_elem_addr(s_h, row, fs.geo_off + k - 1), __half_as_ushort(hv[k]));
+            }
+            fence_proxy_async();
+            fence_before_sync();
+            mbar_arrive(bar_ready);
+
+            // ---------------- LiDAR head ----------------
+            const float4 *bias = reinterpret_cast<const float4 *>(ray_bias + (size_t)rid * kHid);
+            for (uint32_t layer = 0; layer <= sh.n_hid; ++layer) {
+                mbar_wait(bar_done, par);
+                par ^= 1;
+                fence_after_sync();
+                uint4 pk[4];
+                epilogue_relu(d_mine, half, layer == 0 ? bias : nullptr, pk);
+                epi_sync();
+#pragma unroll
+                for (uint32_t c = 0; c < 4; ++c) sts128(tile_chunk_addr(s_h, row, half * 4 + c), pk[c]);
+                fence_proxy_async();
+                fence_before_sync();
+                mbar_arrive(bar_ready);
+                epi_sync();
+                store_tile_rows_256(t256, s_h, fb_h + ((size_t)layer * B + row0) * kHid);
+            }
+
+            // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
+            mbar_wait(bar_done, par);
+            par ^= 1;
+            fence_after_sync();
+            if (half == 0) {
+                uint32_t v[16];
+                tmem_ld16(d_out + lane_sel, v);
+                tmem_ld_wait();
+                const float a = __half2float(__float2half_rn(__uint_as_float(v[0])));
+                const float b = __half2float(__float2half_rn(__uint_as_float(v[1])));
+                reinterpret_cast<float2 *>(rgb)[r] = make_float2(1.f / (1.f + __expf(-a)), 1.f / (1.f + __expf(-b)));
+            }
+            fence_before_sync();   // orders this tile's TMEM reads before the next tile's MMAs (released by `ready`)
         }
-        fence_before_sync();
     }
 
     __syncthreads();
-    if (warp == 0) tmem_dealloc(tmem, 128);
+    if (warp == kMmaWarp) tmem_dealloc(tmem, 128);
 }
 
 int make_shape(uint32_t in_dim, uint32_t nl, Shape *sh) {
@@ -356,9 +394,9 @@ int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, 
     cudaError_t e = cudaFuncSetAttribute(k_field_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
     const uint32_t per_sm = (uint32_t)((227 * 1024) / (smem + 1024));
-    const uint32_t cap = (uint32_t)sm_count_field() * (per_sm < 1 ? 1u : (per_sm > 4 ? 4u : per_sm));
+    const uint32_t cap = (uint32_t)sm_count_field() * (per_sm < 1 ? 1u : (per_sm > 3 ? 3u : per_sm));
     const uint32_t tiles = M / kRows;
-    k_field_fwd<<<tiles < cap ? tiles : cap, kThreads, smem, as_stream(stream)>>>(
+    k_field_fwd<<<tiles < cap ? tiles : cap, kFwdThreads, smem, as_stream(stream)>>>(
         static_cast<const __half *>(enc), static_cast<const __half *>(w_sigma), static_cast<const __half *>(w_head),
         ray_ids, ray_bias, M, fs, density_scale, static_cast<__half *>(fb_sigma), static_cast<__half *>(sig_out), sigma,
         static_cast<__half *>(fb_head), rgb, n_active);

@@ -92,6 +92,14 @@ __device__ __forceinline__ void tg_sync(uint32_t tg) {
     asm volatile("bar.sync %0, 256;" ::"r"(tg + 1) : "memory");
 }
 // cooperative movers for ONE tile group (256 threads, gtid = thread index inside the group)
+// one 128 x 64 tile whose rows are 128 B apart in global memory (saved activations): no division, 4 copies per thread
+__device__ __forceinline__ void tg_load_tile64(uint32_t gtid, uint32_t tile, const __half *__restrict__ src) {
+#pragma unroll
+    for (uint32_t j = 0; j < (kRows * 8) / kTGThreads; ++j) {
+        const uint32_t q = gtid + j * kTGThreads;
+        cp_async16(tile_chunk_addr(tile, q >> 3, q & 7), src + (size_t)q * 8);
+    }
+}
 __device__ __forceinline__ void tg_load_tiles(uint32_t gtid, uint32_t tile0, const __half *__restrict__ src,
                                               uint32_t cols, uint32_t ld) {
     const uint32_t kt = (cols + 63) / 64;
@@ -111,26 +119,17 @@ __device__ __forceinline__ void tg_store_tile_rows(uint32_t gtid, uint32_t tile,
     }
 }
 
-// bit i of the result = (column 32 * half + i of this row of the activation tile) > 0
-__device__ __forceinline__ uint32_t relu_mask_bits(uint32_t tile, uint32_t row, uint32_t half) {
-    uint32_t m = 0u;
+// ReLU mask of this thread's 32 columns of an activation tile as 16 SIMD words (0xffff per half that is > 0;
+// activations are >= 0, so a signed 16-bit compare against zero is exact)
+__device__ __forceinline__ void relu_mask_words(uint32_t tile, uint32_t row, uint32_t half, uint32_t (&m)[16]) {
 #pragma unroll
     for (uint32_t c = 0; c < 4; ++c) {
         const uint4 hv = lds128(tile_chunk_addr(tile, row, half * 4 + c));
-        const uint32_t w[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-        for (uint32_t e = 0; e < 4; ++e) {
-            const uint32_t gt = __vcmpgts2(w[e], 0u);                  // 0xffff per half that is > 0 (activations are >= 0)
-            const uint32_t two = (gt & 1u) | ((gt >> 15) & 2u);
-            m |= two << ((c * 4 + e) * 2);
-        }
+        m[c * 4 + 0] = __vcmpgts2(hv.x, 0u);
+        m[c * 4 + 1] = __vcmpgts2(hv.y, 0u);
+        m[c * 4 + 2] = __vcmpgts2(hv.z, 0u);
+        m[c * 4 + 3] = __vcmpgts2(hv.w, 0u);
     }
-    return m;
-}
-// two accumulator columns -> masked fp16 pair; `two` holds the two mask bits in its low bits
-__device__ __forceinline__ uint32_t masked_pair(uint32_t a, uint32_t b, uint32_t two) {
-    const uint32_t keep = ((0u - (two & 1u)) & 0xffffu) | ((0u - ((two >> 1) & 1u)) << 16);
-    return pack_half2(__uint_as_float(a), __uint_as_float(b)) & keep;
 }
 
 template <bool kHead, uint32_t kGeoWin, uint32_t kGeoIdx, uint32_t kTG>
@@ -145,7 +144,7 @@ k_mlp_bwd(const BwdArgs a) {
     const uint32_t s_win = sbase;
     const uint32_t s_whid = s_win + sh.kt_in * kWTileBytes;
     const uint32_t s_wout = s_whid + sh.n_hid * kWTileBytes;
-    const uint32_t tg_bytes = (1 + n_act + sh.kt_in) * kTileBytes;        // G (aliased by dH), activations, X
+    const uint32_t tg_bytes = (2 + n_act + sh.kt_in) * kTileBytes;        // G/dH ping-pong pair, activations, X
     const uint32_t s_tg0 = s_wout + 2048;
     const uint32_t s_bar = s_tg0 + kTG * tg_bytes;                        // ready[2], done[2], fin, slot
 
@@ -208,7 +207,10 @@ k_mlp_bwd(const BwdArgs a) {
                     const uint32_t tile = (it * gridDim.x + blockIdx.x) * kTG + g;
                     if (tile >= n_tiles) continue;
                     const uint32_t base = s_tg0 + g * tg_bytes;
-                    const uint32_t s_g = base, s_d = base, s_h = base + kTileBytes;   // dH overwrites G
+                    // phase p reads the gradient tile (p & 1); the epilogue that follows writes tile ((p + 1) & 1), so it
+                    // never waits for this phase's weight-gradient MMAs, which keep reading tile (p & 1)
+                    const uint32_t s_cur = base + ((ph <= sh.n_hid + 1 ? ph : sh.n_hid + 1) & 1u) * kTileBytes;
+                    const uint32_t s_h = base + 2 * kTileBytes;
                     const uint32_t s_x = s_h + n_act * kTileBytes;
                     const uint32_t d_acc = tmem + 64 * g;
                     mbar_wait_warp(bar_ready0 + 8 * g, par_ready[g]);
@@ -218,22 +220,26 @@ k_mlp_bwd(const BwdArgs a) {
                     // group 0 of a CTA that owns any tile is served first in iteration 0: it initialises the accumulators
                     const bool accw = !(it == 0 && g == 0);
                     if (ph == 0) {
-                        issue_dgrad(d_acc, s_g, s_wout, 1);
-                        issue_wgrad(d_wout, s_h + sh.n_hid * kTileBytes, s_g, accw, 16);
+                        issue_dgrad(d_acc, s_cur, s_wout, 1);
+                        mma_commit_elect(bar_done0 + 8 * g);     // the epilogue needs only the dgrad accumulator
+                        issue_wgrad(d_wout, s_h + sh.n_hid * kTileBytes, s_cur, accw, 16);
                     } else if (ph <= sh.n_hid) {
-                        const uint32_t layer = sh.n_hid - ph + 1;        // dpre of h_layer is in s_d
-                        issue_dgrad(d_acc, s_d, s_whid + (layer - 1) * kWTileBytes, 4);
-                        issue_wgrad(d_whid + 64 * (layer - 1), s_d, s_h + (layer - 1) * kTileBytes, accw);
+                        const uint32_t layer = sh.n_hid - ph + 1;        // dpre of h_layer is in s_cur
+                        issue_dgrad(d_acc, s_cur, s_whid + (layer - 1) * kWTileBytes, 4);
+                        mma_commit_elect(bar_done0 + 8 * g);
+                        issue_wgrad(d_whid + 64 * (layer - 1), s_cur, s_h + (layer - 1) * kTileBytes, accw);
                     } else if (ph == sh.n_hid + 1) {
-                        // dW_in: the X tiles are consecutive in shared memory -> ONE group of N = win_cols (<= 128)
-                        issue_wgrad(d_win, s_d, s_x, accw, win_cols);
-                        if (kHead) issue_dgrad(d_acc, s_d, s_win + a.geo_tile * kWTileBytes, 4);   // geo tile of dX only
-                        else if (want_dx) issue_dgrad(d_acc, s_d, s_win, 4);
+                        // dW_in: the X tiles are consecutive in shared memory -> ONE group of N = win_cols (<= 128).
+                        // Last phase of the tile: one commit covers every MMA issued for it (tensor pipe is in order).
+                        issue_wgrad(d_win, s_cur, s_x, accw, win_cols);
+                        if (kHead) issue_dgrad(d_acc, s_cur, s_win + a.geo_tile * kWTileBytes, 4);   // geo tile of dX only
+                        else if (want_dx) issue_dgrad(d_acc, s_cur, s_win, 4);
+                        mma_commit_elect(bar_done0 + 8 * g);
                     } else {
                         const uint32_t t = ph - sh.n_hid - 1;            // 1 .. kt_in-1
-                        issue_dgrad(d_acc, s_d, s_win + t * kWTileBytes, 4);
+                        issue_dgrad(d_acc, s_cur, s_win + t * kWTileBytes, 4);
+                        mma_commit_elect(bar_done0 + 8 * g);
                     }
-                    mma_commit_elect(bar_done0 + 8 * g);
                     if (lane == 0) LNB_TR(2u, 3u + g, ph);
                 }
             }
@@ -247,7 +253,8 @@ k_mlp_bwd(const BwdArgs a) {
         const uint32_t gtid = threadIdx.x & 255u;
         const bool tracer = gtid == 0;
         const uint32_t base = s_tg0 + tg * tg_bytes;
-        const uint32_t s_g = base, s_d = base, s_h = base + kTileBytes;   // dH overwrites G after phase 0
+        const uint32_t s_g = base;                           // gradient tiles: phase p reads base + (p & 1) tiles
+        const uint32_t s_h = base + 2 * kTileBytes;
         const uint32_t s_x = s_h + n_act * kTileBytes;
         const uint32_t d_mine = tmem + 64 * tg + 32 * half + (((warp & 3u) * 32u) << 16);
         const uint32_t bar_ready = bar_ready0 + 8 * tg, bar_done = bar_done0 + 8 * tg;
@@ -264,7 +271,7 @@ k_mlp_bwd(const BwdArgs a) {
             h.gs = __ldg(a.g_sigma + r);
         };
         auto load_act = [&](uint32_t layer, uint32_t tile) {
-            tg_load_tiles(gtid, s_h + layer * kTileBytes, a.fbuf + ((size_t)layer * B + (size_t)tile * kRows) * kHid, kHid, kHid);
+            tg_load_tile64(gtid, s_h + layer * kTileBytes, a.fbuf + ((size_t)layer * B + (size_t)tile * kRows) * kHid);
         };
         // inputs that live in the X / G tiles: free once the last MMA of the previous tile has retired
         auto load_xg = [&](uint32_t tile, const HeadRow &h) {
@@ -274,7 +281,7 @@ k_mlp_bwd(const BwdArgs a) {
                 for (uint32_t c = half; c < n_enc_chunks; c += 2)               // the row's two threads alternate chunks
                     cp_async16(tile_chunk_addr(s_x + (c >> 3) * kTileBytes, row, c & 7), enc_row + c * 8);
             } else {
-                // G: 16 valid columns (chunks 0,1); chunks 2..7 re-zeroed every tile because dH aliases this tile
+                // G: 16 valid columns (chunks 0,1); chunks 2..7 re-zeroed every tile because dH reuses this tile
                 for (uint32_t q = gtid; q < kRows * 8; q += kTGThreads) {
                     const uint32_t r = q >> 3, c = q & 7;
                     cp_async16(tile_chunk_addr(s_g, r, c), a.G + (row0 + r) * kOut + (c < 2 ? c * 8 : 0), c < 2 ? 16u : 0u);
@@ -324,12 +331,8 @@ k_mlp_bwd(const BwdArgs a) {
             fence_before_sync();
             mbar_arrive(bar_ready);       // phase-0 operands of this thread are in place
             if (tracer) LNB_TR(tg, 2u, 0u);
-            // while the tensor core runs phase 0: ReLU masks of every layer into registers, next tile's row inputs
-            tg_sync(tg);                  // every thread's copies of this tile have landed
-            const uint32_t m0 = relu_mask_bits(s_h, row, half);
-            const uint32_t m1 = n_act > 1 ? relu_mask_bits(s_h + kTileBytes, row, half) : 0u;
-            const uint32_t m2 = n_act > 2 ? relu_mask_bits(s_h + 2 * kTileBytes, row, half) : 0u;
-            tg_sync(tg);                  // all mask reads done before any activation tile is refilled
+            tg_sync(tg);                  // every thread's copies of this tile have landed (mask reads below)
+            if (tracer) LNB_TR(tg, 8u, 0u);
             const uint32_t next = tile + stride_tiles;
             const bool have_next = next < n_tiles;
             HeadRow hn = {};
@@ -337,6 +340,9 @@ k_mlp_bwd(const BwdArgs a) {
 
             // ---- layers, last to first: epilogue = ReLU mask, fp16, operand for the next MMA ----
             for (int layer = (int)sh.n_hid; layer >= 0; --layer) {
+                // while the tensor core works: this layer's ReLU mask (the tile is refilled only after a LATER phase)
+                uint32_t m[16];
+                relu_mask_words(s_h + (uint32_t)layer * kTileBytes, row, half, m);
                 mbar_wait(bar_done, par_done);
                 par_done ^= 1;
                 fence_after_sync();
@@ -345,15 +351,16 @@ k_mlp_bwd(const BwdArgs a) {
                 tmem_ld32(d_mine, v);
                 tmem_ld_wait();
                 if (tracer) LNB_TR(tg, 4u, (uint32_t)layer);
-                const uint32_t m = layer == 0 ? m0 : (layer == 1 ? m1 : m2);
+                const uint32_t ph = sh.n_hid - (uint32_t)layer;             // phase whose dgrad accumulator this is
+                const uint32_t s_out = base + ((ph + 1u) & 1u) * kTileBytes;   // gradient tile the next phase reads
 #pragma unroll
                 for (uint32_t c = 0; c < 4; ++c) {
                     uint4 pk;
-                    pk.x = masked_pair(v[c * 8 + 0], v[c * 8 + 1], m >> (c * 8 + 0));
-                    pk.y = masked_pair(v[c * 8 + 2], v[c * 8 + 3], m >> (c * 8 + 2));
-                    pk.z = masked_pair(v[c * 8 + 4], v[c * 8 + 5], m >> (c * 8 + 4));
-                    pk.w = masked_pair(v[c * 8 + 6], v[c * 8 + 7], m >> (c * 8 + 6));
-                    sts128(tile_chunk_addr(s_d, row, half * 4 + c), pk);
+                    pk.x = pack_half2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1])) & m[c * 4 + 0];
+                    pk.y = pack_half2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3])) & m[c * 4 + 1];
+                    pk.z = pack_half2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5])) & m[c * 4 + 2];
+                    pk.w = pack_half2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7])) & m[c * 4 + 3];
+                    sts128(tile_chunk_addr(s_out, row, half * 4 + c), pk);
                 }
                 if (tracer) LNB_TR(tg, 5u, (uint32_t)layer);
                 fence_proxy_async();
@@ -361,12 +368,13 @@ k_mlp_bwd(const BwdArgs a) {
                 mbar_arrive(bar_ready);
                 if (tracer) LNB_TR(tg, 6u, (uint32_t)layer);
                 if (!kHead && a.bbuf) {
-                    tg_sync(tg);   // every row of s_d written
-                    tg_store_tile_rows(gtid, s_d, a.bbuf + ((size_t)(sh.n_hid - layer) * B + row0) * kHid);
-                    tg_sync(tg);   // all readers done before the next epilogue rewrites s_d
+                    tg_sync(tg);   // every row of the tile written
+                    tg_store_tile_rows(gtid, s_out, a.bbuf + ((size_t)(sh.n_hid - layer) * B + row0) * kHid);
+                    tg_sync(tg);   // all readers done before a later epilogue rewrites it
                 }
-                // this layer's saved-activation tile is dead (its wgrad retired before `done`): fetch the next tile's
-                if (have_next) load_act((uint32_t)layer, next);
+                // The `done` we just consumed retires every EARLIER MMA of this group (in-order pipe), in particular
+                // the previous phase's weight-gradient MMAs that read saved-activation tile layer + 1: refill it now.
+                if (have_next && layer < (int)sh.n_hid) load_act((uint32_t)layer + 1, next);
             }
             if (kHead) {
                 // ---- geo gradient + density gradient -> g_sig_out row (network.py:173 trunc_exp backward) ----
@@ -421,8 +429,12 @@ k_mlp_bwd(const BwdArgs a) {
                 }
             }
             if (tracer) LNB_TR(tg, 7u, 0u);
-            // every MMA of this tile has retired (last `done` wait above): its X / G tiles can take the next tile
-            if (have_next) load_xg(next, hn);
+            // every MMA of this tile has retired (last `done` wait above): activation tile 0 and the X / G tiles can
+            // take the next tile
+            if (have_next) {
+                load_act(0, next);
+                load_xg(next, hn);
+            }
             fence_before_sync();          // orders this tile's TMEM reads before the next tile's MMAs
             hr = hn;
             tile = next;
@@ -482,7 +494,7 @@ k_mlp_bwd(const BwdArgs a) {
 
 inline size_t mlp_bwd_smem(const Shape &sh, uint32_t tg) {
     return 1024 + (size_t)sh.kt_in * kWTileBytes + (size_t)sh.n_hid * kWTileBytes + 2048 +
-           (size_t)tg * (1 + sh.n_hid + 1 + sh.kt_in) * kTileBytes + 64;
+           (size_t)tg * (2 + sh.n_hid + 1 + sh.kt_in) * kTileBytes + 64;
 }
 
 template <bool kHead, uint32_t kGeoWin, uint32_t kGeoIdx, uint32_t kTG>
@@ -506,9 +518,9 @@ int launch_mlp_bwd(const BwdArgs &a, uint32_t sm_count, cudaStream_t st) {
     // independent 288-thread CTAs (109/101 us vs 118/114 us for head / density MLP) - the M = 64 weight-gradient MMAs
     // (both operands from shared memory) occupy the tensor pipe ~150 cycles each, so a second issuing warp buys
     // nothing.  The single-tile variant remains for shapes whose tiles / accumulators do not fit twice.
-    if (bwd_tmem_cols(a.sh, 2, win_cols) <= 512 && mlp_bwd_smem(a.sh, 2) <= 220 * 1024)
+    if (bwd_tmem_cols(a.sh, 2, win_cols) <= 512 && mlp_bwd_smem(a.sh, 2) <= 226 * 1024)
         return launch_mlp_bwd_tg<kHead, kGeoWin, kGeoIdx, 2>(a, sm_count, st);
-    if (bwd_tmem_cols(a.sh, 1, win_cols) > 512 || mlp_bwd_smem(a.sh, 1) > 220 * 1024) return LNB_ERR_UNSUPPORTED;
+    if (bwd_tmem_cols(a.sh, 1, win_cols) > 512 || mlp_bwd_smem(a.sh, 1) > 226 * 1024) return LNB_ERR_UNSUPPORTED;
     return launch_mlp_bwd_tg<kHead, kGeoWin, kGeoIdx, 1>(a, sm_count, st);
 }
 

@@ -18,7 +18,7 @@ from lidar_nerf_b200 import _lib   # noqa: E402
 from lidar_nerf_b200.nerf.engine import LidarFieldEngine, FieldConfig   # noqa: E402
 from lidar_nerf_b200.data.synthetic import SyntheticLidarSequence       # noqa: E402
 
-EV = {0: "top", 1: "landed", 2: "arrive0", 3: "done", 4: "tmem", 5: "sts", 6: "arrive", 7: "tile_end"}
+EV = {0: "top", 1: "landed", 2: "arrive0", 3: "done", 4: "tmem", 5: "sts", 6: "arrive", 7: "tile_end", 8: "synced"}
 MMA = {1: "ready g0", 2: "ready g1", 3: "issued g0", 4: "issued g1"}
 
 
