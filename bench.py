@@ -39,6 +39,9 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="launch the step eagerly (for ncu, which cannot replay the 187 KB-smem MLP backward as a captured graph node)")
+    ap.add_argument("--profiler-range", action="store_true",
+                    help="for ncu --profile-from-start off: cudaProfilerStart/Stop around the timed steps, then exit "
+                         "(numbers printed under a profiler are not bench values)")
     ap.add_argument("--cpu-rays", type=int, default=512, help="rays per CPU-baseline step (bounded sample)")
     ap.add_argument("--cpu-steps", type=int, default=3)
     return ap.parse_args()
@@ -249,11 +252,17 @@ def main():
     barrier()
     clocks.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if args.profiler_range:
+        torch.cuda.profiler.start()
     e0.record()
     run(args.steps, False)
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
+    if args.profiler_range:
+        torch.cuda.profiler.stop()
+        print(json.dumps({"profiler_range": True, "steps": args.steps, "ms_per_step_under_profiler": ms / args.steps}))
+        return 0
     launches = _lib.launch_count() - launches0
     produced, _ = eng.samples_last_step()
 
