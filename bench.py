@@ -382,7 +382,7 @@ def profile_kernels(eng, pool, load, iters=5):
                       (E.rm, "composite_rays_train_backward_ex"), (E.ff, "ffmlp_forward")):
         saved.append((obj, name, wrap(obj, name, name)))
     lib_names = ["lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_ray_terms", "lnb_field_forward",
-                 "lnb_field_head_backward",
+                 "lnb_field_head_backward", "lnb_lidar_composite_step",
                  "lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_ffmlp_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
                  "lnb_lidar_loss", "lnb_field_head_out_grad", "lnb_ffmlp_backward_accumulate", "lnb_field_sigma_out_grad",
                  "lnb_grid_encode_backward_ex"]

@@ -79,7 +79,9 @@ int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
 
 /* Extension: additionally writes ray_ids [M] (nullable) = rays_o/rays_d row each sample belongs to, and accepts
  * dirs == NULL when ray_ids is given (all samples of a ray share its direction; the fused field kernels below look
- * the direction terms up per ray instead of reading 12 B per sample). */
+ * the direction terms up per ray instead of reading 12 B per sample).  It also zeroes the rows of xyzs / dirs /
+ * deltas / ray_ids between the produced total counter[0] and the next multiple of 128 (capped at M): the padding of
+ * the last 128-row tile that the per-sample kernels process (what lnb_zero_sample_tail_ex does as a separate launch). */
 int lnb_march_rays_train_ex(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                             uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
@@ -273,6 +275,20 @@ int lnb_field_head_rgb(const void *head_out, uint32_t M, float *rgb, const int32
 int lnb_lidar_loss(const float *weights_sum, const float *depth, const float *image, const float *gt,
                    const float *t0, uint32_t N, float alpha_d, float alpha_r, float alpha_i, float loss_scale,
                    float *g_weights_sum, float *g_depth, float *g_image, float *loss_out, lnb_stream_t stream);
+/* One kernel for lnb_composite_rays_train_forward_ex (2 channels) -> lnb_lidar_loss -> lnb_composite_rays_train_
+ * backward_ex with the depth gradient: the warp that composites a ray keeps its (weights_sum, depth, image) in
+ * registers, evaluates the loss terms of that ray and walks the ray's samples again for the backward pass.
+ * Replaces raymarching.cu:578-802 + nerf/utils.py:726-734 in the fused training step.  Every sample of every
+ * marched ray receives a gradient (zero behind the early stop) and the rows between counter[0] and the next
+ * multiple of 128 are zeroed, so grad_sigmas / grad_rgbs need no zero fill.  The march start of each ray,
+ * near + clamp(near * dt_gamma, dt_min, dt_max) * noise (raymarching.cu:369-375), is recomputed from
+ * (nears, noises, dt_gamma, max_steps, C, H) and written to t0 [N] (nullable).  loss_out[0] += loss. */
+int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                              const float *gt, const float *nears, const float *noises, float dt_gamma,
+                              uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
+                              uint32_t N, float T_thresh, float alpha_d, float alpha_r, float alpha_i,
+                              float loss_scale, float *weights_sum, float *depth, float *image, float *t0,
+                              float *grad_sigmas, float *grad_rgbs, float *loss_out, lnb_stream_t stream);
 int lnb_field_head_out_grad(const float *g_rgb, const float *rgb, uint32_t M, void *g_head_out,
                             const int32_t *n_active, lnb_stream_t stream);
 int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const void *g_head_in, uint32_t M,

@@ -41,7 +41,7 @@ SYMBOLS = [
     "lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_supported", "lnb_field_ray_terms",
     "lnb_field_forward", "lnb_field_head_backward",
     "lnb_zero_sample_tail", "lnb_field_head_input", "lnb_field_head_rgb", "lnb_lidar_loss",
-    "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays",
+    "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays", "lnb_lidar_composite_step",
 ]
 
 

@@ -234,9 +234,14 @@ k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const _
                 mbar_wait(bar_done, par);
                 par ^= 1;
                 fence_after_sync();
-                if (layer == 0 && tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's features
-                    load(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * ss.in_dim, kRows, ss.in_dim, ss.in_dim, false,
-                         t256, kFwdEpiThreads);
+                if (layer == 0) {
+                    if (tile + gridDim.x < n_tiles)   // s_x is free: prefetch the next tile's features
+                        load(s_x, kTileBytes, X + (size_t)(tile + gridDim.x) * kRows * ss.in_dim, kRows, ss.in_dim,
+                             ss.in_dim, false, t256, kFwdEpiThreads);
+                    // this thread's 128 B of the per-ray head bias, needed four layers from now: pull the line into L1
+                    // (the profile showed the head's first epilogue stalled on exactly this L2 round trip)
+                    asm volatile("prefetch.global.L1 [%0];" ::"l"(ray_bias + (size_t)rid * kHid + half * 32));
+                }
                 uint4 pk[4];
                 epilogue_relu(d_mine, half, nullptr, pk);
                 epi_sync();                                   // the previous layer's tile has been streamed out

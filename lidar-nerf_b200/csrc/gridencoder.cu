@@ -69,6 +69,73 @@ __device__ __forceinline__ uint32_t cell_row(const uint32_t (&p)[D], uint32_t gr
     return index % g.hashmap_size;
 }
 
+// Per-level, per-sample row indexing with the level-uniform decisions of cell_row() hoisted out of the corner loop
+// (the profile of the first version showed the generic `% hashmap_size` and the stride tests, repeated for each
+// of the 2^D corners, as 15-20 % of both the gather and the scatter kernel).  Three cases, same results as cell_row():
+//   dense   every dimension fits and side^D <= hashmap_size: row = sum p_d * stride_d, can never wrap;
+//   hashed  with a power-of-two table (every hashed level the reference's sizing produces, grid.py:179-192):
+//           row = xor p_d * prime_d, masked;
+//   anything else (tiled grids that wrap, odd table sizes): the generic cell_row().
+template <uint32_t D>
+struct LevelIndex {
+    uint32_t mul[D];
+    uint32_t mask;      // all ones for dense levels
+    bool hashed, generic;
+};
+
+template <uint32_t D>
+__device__ __forceinline__ LevelIndex<D> level_index(const LevelGeo &g, uint32_t gridtype, bool align_corners) {
+    constexpr uint32_t kPrimes[7] = {1u, 2654435761u, 805459861u, 3674653429u,
+                                     2097192037u, 1434869437u, 2165219737u};
+    LevelIndex<D> li;
+    const uint32_t side = align_corners ? g.resolution : (g.resolution + 1);
+    uint32_t stride = 1;
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        if (stride <= g.hashmap_size) {
+            li.mul[d] = stride;
+            stride *= side;
+        } else {
+            li.mul[d] = 0;
+        }
+    }
+    li.hashed = (gridtype == 0 && stride > g.hashmap_size);
+    const bool pow2 = (g.hashmap_size & (g.hashmap_size - 1)) == 0;
+    li.generic = li.hashed ? !pow2 : (stride > g.hashmap_size);
+    li.mask = li.hashed ? g.hashmap_size - 1 : 0xffffffffu;
+    if (li.hashed) {
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) li.mul[d] = kPrimes[d];
+    }
+    return li;
+}
+
+// the two per-dimension terms (base, base + 1) of one sample on one level; row(corner) combines D of them
+template <uint32_t D>
+struct CornerRows {
+    uint32_t t[D][2];
+    uint32_t mask;
+    bool hashed;
+    __device__ __forceinline__ CornerRows(const LevelIndex<D> &li, const uint32_t (&base)[D]) {
+        mask = li.mask;
+        hashed = li.hashed;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+            t[d][0] = base[d] * li.mul[d];
+            t[d][1] = t[d][0] + li.mul[d];
+        }
+    }
+    __device__ __forceinline__ uint32_t row(uint32_t corner) const {
+        uint32_t v = t[0][corner & 1u];
+#pragma unroll
+        for (uint32_t d = 1; d < D; ++d) {
+            const uint32_t u = t[d][(corner >> d) & 1u];
+            v = hashed ? (v ^ u) : (v + u);
+        }
+        return v & mask;
+    }
+};
+
 template <uint32_t D>
 struct Cell {
     uint32_t base[D];
@@ -144,8 +211,62 @@ __device__ __forceinline__ void load_row(const T *__restrict__ p, float (&v)[C])
     }
 }
 
-// Forward.  Accumulates in the table's type exactly like the reference (`scalar_t results[C]`,
-// gridencoder.cu:173-199): every `+= w * grid[...]` is rounded to T.
+// one table row with the widest load its size allows, left in the table's type
+template <typename T, uint32_t C>
+__device__ __forceinline__ void load_row_raw(const T *__restrict__ p, T (&v)[C]) {
+    constexpr uint32_t kBytes = sizeof(T) * C;
+    if constexpr (kBytes == 4) {
+        *reinterpret_cast<uint32_t *>(v) = __ldg(reinterpret_cast<const uint32_t *>(p));
+    } else if constexpr (kBytes == 8) {
+        *reinterpret_cast<uint2 *>(v) = __ldg(reinterpret_cast<const uint2 *>(p));
+    } else if constexpr (kBytes % 16 == 0) {
+#pragma unroll
+        for (uint32_t i = 0; i < kBytes / 16; ++i)
+            reinterpret_cast<uint4 *>(v)[i] = __ldg(reinterpret_cast<const uint4 *>(p) + i);
+    } else {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) v[c] = __ldg(p + c);
+    }
+}
+
+// sum over the 2^D corners of w_corner * table[row(corner)], accumulated in the table's type exactly like the
+// reference (`scalar_t results[C]`, gridencoder.cu:173-199): every `+= w * grid[...]` is rounded to T.
+template <typename T, uint32_t D, uint32_t C, bool kGeneric>
+__device__ __forceinline__ void interp_corners(const Cell<D> &cell, const LevelGeo &g, const LevelIndex<D> &li,
+                                               uint32_t gridtype, bool align_corners, const T *__restrict__ tab,
+                                               T (&res)[C]) {
+    const CornerRows<D> cr(li, cell.base);
+    // all gathers first (2^D independent loads in flight, kept in the table's type), then the rounding-ordered
+    // accumulation
+    __align__(16) T v[1u << D][C];
+#pragma unroll
+    for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+        uint32_t row;
+        if (kGeneric) {
+            uint32_t p[D];
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) p[d] = cell.base[d] + ((corner >> d) & 1u);
+            row = cell_row<D>(p, gridtype, align_corners, g);
+        } else {
+            row = cr.row(corner);
+        }
+        load_row_raw<T, C>(tab + (size_t)row * C, v[corner]);
+    }
+#pragma unroll
+    for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+        float w = 1;
+#pragma unroll
+        for (uint32_t d = 0; d < D; ++d) {
+            if ((corner & (1u << d)) == 0) w *= 1 - cell.frac[d];
+            else w *= cell.frac[d];
+        }
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c)
+            res[c] = Num<T>::from_f(Num<T>::to_f(res[c]) + w * Num<T>::to_f(v[corner][c]));
+    }
+}
+
+// Forward.
 template <typename T, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(kFwdThreads, 3)
 k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
@@ -153,6 +274,7 @@ k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
            float S, uint32_t H, T *__restrict__ dy_dx, uint32_t gridtype, bool align_corners,
            uint32_t interp, int layout, float2 norm, const int32_t *__restrict__ n_active) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ float s_in[kTileB * D];   // the tile's coordinates mapped to [0,1]: every warp (= level) reads all of them
     B = (layout == LNB_LAYOUT_LBC) ? B : active_rows(B, n_active);   // [L,B,C] addressing needs the true B
     if (blockIdx.x * kTileB >= B) return;
     T *tile = reinterpret_cast<T *>(smem_raw);  // [kTileB][pitch], only for LNB_LAYOUT_BLC
@@ -161,43 +283,45 @@ k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
     const uint32_t b0 = blockIdx.x * kTileB;
+    {
+        const uint32_t n_in = min((uint32_t)kTileB, B - b0) * D;
+        const float *src = inputs + (size_t)b0 * D;
+        for (uint32_t i = threadIdx.x; i < kTileB * D; i += blockDim.x) {
+            float x = 0.f;
+            if (i < n_in) {
+                x = __ldg(src + i);
+                if (norm.x != 0.f) x = (x + norm.x) * norm.y;
+            }
+            s_in[i] = x;
+        }
+    }
+    __syncthreads();
 
     for (uint32_t level = warp; level < L; level += n_warps) {
         const LevelGeo g = level_geo(offsets, level, S, H);
+        const LevelIndex<D> li = level_index<D>(g, gridtype, align_corners);
         const T *__restrict__ tab = table + (size_t)g.table_offset * C;
 #pragma unroll
         for (uint32_t grp = 0; grp < kTileB / 32; ++grp) {
             const uint32_t sl = grp * 32 + lane;
             const uint32_t b = b0 + sl;
             if (b >= B) continue;
-            const Cell<D> cell = locate<D>(inputs + (size_t)b * D, g, align_corners, interp, norm);
+            float v[D];
+            bool inside = true;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                v[d] = s_in[sl * D + d];
+                if (v[d] < 0 || v[d] > 1) inside = false;
+            }
+            const Cell<D> cell = locate_unit<D>(v, inside, g, align_corners, interp);
 
             T res[C];
 #pragma unroll
             for (uint32_t c = 0; c < C; ++c) res[c] = Num<T>::from_f(0.f);
 
             if (cell.inside) {
-#pragma unroll
-                for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-                    float w = 1;
-                    uint32_t p[D];
-#pragma unroll
-                    for (uint32_t d = 0; d < D; ++d) {
-                        if ((corner & (1u << d)) == 0) {
-                            w *= 1 - cell.frac[d];
-                            p[d] = cell.base[d];
-                        } else {
-                            w *= cell.frac[d];
-                            p[d] = cell.base[d] + 1;
-                        }
-                    }
-                    const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
-                    float v[C];
-                    load_row<T, C>(tab + (size_t)row * C, v);
-#pragma unroll
-                    for (uint32_t c = 0; c < C; ++c)
-                        res[c] = Num<T>::from_f(Num<T>::to_f(res[c]) + w * v[c]);
-                }
+                if (li.generic) interp_corners<T, D, C, true>(cell, g, li, gridtype, align_corners, tab, res);
+                else interp_corners<T, D, C, false>(cell, g, li, gridtype, align_corners, tab, res);
             }
 
             if (layout == LNB_LAYOUT_LBC) {
@@ -306,15 +430,38 @@ __device__ __forceinline__ void atomic_add_one(float *p, float a) { atomicAdd(p,
 // 2^D corner contributions are summed over the run with a segmented shuffle scan and only the run's last lane issues
 // the atomics (exact up to fp32 summation order).  A zero gradient row adds nothing and is skipped (padding samples
 // all sit at one position and would otherwise serialise tens of thousands of atomics on the same rows).
+constexpr uint32_t kMaxLevelsShared = 32;
+
+template <typename TG, uint32_t C>
+__device__ __forceinline__ void load_grad_row(const TG *__restrict__ gp, float (&gv)[C]) {
+    if constexpr (sizeof(TG) == 2 && C % 2 == 0) {
+#pragma unroll
+        for (uint32_t c = 0; c < C; c += 2) {
+            const float2 f = __half22float2(__ldg(reinterpret_cast<const __half2 *>(gp + c)));
+            gv[c] = f.x, gv[c + 1] = f.y;
+        }
+    } else {
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) gv[c] = Num<TG>::to_f(__ldg(gp + c));
+    }
+}
+
 template <typename TG, typename TA, uint32_t D, uint32_t C>
 __global__ void __launch_bounds__(kBwdThreads)
 k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
            const int32_t *__restrict__ offsets, TA *__restrict__ grad_table, uint32_t B, uint32_t L,
            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout, float2 norm,
            uint32_t n_agg, const int32_t *__restrict__ n_active) {
+    __shared__ LevelGeo s_geo[kMaxLevelsShared];
+    __shared__ LevelIndex<D> s_idx[kMaxLevelsShared];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     const uint32_t Bact = active_rows(B, n_active);
     if (blockIdx.x * blockDim.x >= Bact) return;
+    if (threadIdx.x < min(L, kMaxLevelsShared)) {   // level-uniform quantities, once per CTA
+        const LevelGeo g = level_geo(offsets, threadIdx.x, S, H);
+        s_geo[threadIdx.x] = g;
+        s_idx[threadIdx.x] = level_index<D>(g, gridtype, align_corners);
+    }
     const bool in_range = b < Bact;
     const unsigned lane = lane_id();
 
@@ -325,36 +472,53 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
 #pragma unroll
         for (uint32_t d = 0; d < D; ++d) v[d] = 0.f;
     }
+    const bool has_grad = in_range && inside;
+    const size_t g_stride = (layout == LNB_LAYOUT_LBC) ? (size_t)B * C : (size_t)C;
+    const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + (size_t)b * C : grad + (size_t)b * L * C;
+    float gv_next[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) gv_next[c] = 0.f;
+    if (has_grad) load_grad_row<TG, C>(gp, gv_next);
+    __syncthreads();
 
     for (uint32_t level = 0; level < L; ++level) {
-        const LevelGeo g = level_geo(offsets, level, S, H);
-        const Cell<D> cell = locate_unit<D>(v, inside, g, align_corners, interp);
         float gv[C];
+#pragma unroll
+        for (uint32_t c = 0; c < C; ++c) gv[c] = gv_next[c];
+        if (has_grad && level + 1 < L) load_grad_row<TG, C>(gp + (size_t)(level + 1) * g_stride, gv_next);   // one level ahead
+
+        LevelGeo g;
+        LevelIndex<D> li;
+        if (level < kMaxLevelsShared) {
+            g = s_geo[level];
+            li = s_idx[level];
+        } else {
+            g = level_geo(offsets, level, S, H);
+            li = level_index<D>(g, gridtype, align_corners);
+        }
         bool live = false;
 #pragma unroll
-        for (uint32_t c = 0; c < C; ++c) gv[c] = 0.f;
-        if (in_range && inside) {
-            const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + ((size_t)level * B + b) * C
-                                                      : grad + ((size_t)b * L + level) * C;
-            if constexpr (sizeof(TG) == 2 && C % 2 == 0) {
-#pragma unroll
-                for (uint32_t c = 0; c < C; c += 2) {
-                    const float2 f = __half22float2(__ldg(reinterpret_cast<const __half2 *>(gp + c)));
-                    gv[c] = f.x, gv[c + 1] = f.y;
-                }
-            } else {
-#pragma unroll
-                for (uint32_t c = 0; c < C; ++c) gv[c] = Num<TG>::to_f(__ldg(gp + c));
-            }
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) live |= (gv[c] != 0.f);
-        }
+        for (uint32_t c = 0; c < C; ++c) live |= (gv[c] != 0.f);
         const bool agg = level < n_agg;      // warp-uniform
         if (!agg && !live) continue;
 
-        unsigned run_start = 0;
-        bool tail = true;
+        const Cell<D> cell = locate_unit<D>(v, inside, g, align_corners, interp);
+        float acc[1u << D][C];
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            float w = 1;
+#pragma unroll
+            for (uint32_t d = 0; d < D; ++d) {
+                if ((corner & (1u << d)) == 0) w *= 1 - cell.frac[d];
+                else w *= cell.frac[d];
+            }
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) acc[corner][c] = w * gv[c];
+        }
+
+        bool issue = live;
         if (agg) {
+            // runs = maximal groups of consecutive live lanes in the same cell
             bool head = (lane == 0) || !live;
             const int prev_live = __shfl_up_sync(kFullMask, (int)live, 1);
             if (!prev_live) head = true;
@@ -363,53 +527,47 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
                 const uint32_t pb = __shfl_up_sync(kFullMask, cell.base[d], 1);
                 if (pb != cell.base[d]) head = true;
             }
-            run_start = head ? lane : 0u;
+            const unsigned head_mask = __ballot_sync(kFullMask, head);          // bit 0 is always set
+            const unsigned run_start = 31u - (unsigned)__clz(head_mask & (kFullMask >> (31u - lane)));
+            // segmented inclusive scan over the runs, only as deep as the longest run of this warp needs: the fine
+            // levels (runs of one) pay a ballot and a REDUX, the coarse ones (tens of samples per cell) the full depth
+            const unsigned need = __reduce_max_sync(kFullMask, lane - run_start);
+            for (unsigned o = 1; o <= need; o <<= 1) {
+                const bool take = lane >= run_start + o;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned t = __shfl_up_sync(kFullMask, run_start, o);
-                if (lane >= (unsigned)o) run_start = max(run_start, t);
-            }
-            const int next_head = __shfl_down_sync(kFullMask, (int)head, 1);
-            tail = (lane == 31) || next_head;
-        }
-
-        TA *gt = grad_table + (size_t)g.table_offset * C;
-#pragma unroll
-        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
-            float w = 1;
-            uint32_t p[D];
-#pragma unroll
-            for (uint32_t d = 0; d < D; ++d) {
-                if ((corner & (1u << d)) == 0) {
-                    w *= 1 - cell.frac[d];
-                    p[d] = cell.base[d];
-                } else {
-                    w *= cell.frac[d];
-                    p[d] = cell.base[d] + 1;
-                }
-            }
-            float acc[C];
-#pragma unroll
-            for (uint32_t c = 0; c < C; ++c) acc[c] = w * gv[c];
-            if (agg) {
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
+                for (uint32_t corner = 0; corner < (1u << D); ++corner) {
 #pragma unroll
                     for (uint32_t c = 0; c < C; ++c) {
-                        const float t = __shfl_up_sync(kFullMask, acc[c], o);
-                        if (lane >= run_start + (unsigned)o) acc[c] += t;
+                        const float t = __shfl_up_sync(kFullMask, acc[corner][c], o);
+                        if (take) acc[corner][c] += t;
                     }
                 }
-                if (!(tail && live)) continue;
             }
-            const uint32_t row = cell_row<D>(p, gridtype, align_corners, g);
+            const bool tail = (lane == 31) || ((head_mask >> (lane + 1)) & 1u);
+            issue = tail && live;
+        }
+        if (!issue) continue;
+
+        TA *gt = grad_table + (size_t)g.table_offset * C;
+        const CornerRows<D> cr(li, cell.base);
+#pragma unroll
+        for (uint32_t corner = 0; corner < (1u << D); ++corner) {
+            uint32_t row;
+            if (li.generic) {
+                uint32_t p[D];
+#pragma unroll
+                for (uint32_t d = 0; d < D; ++d) p[d] = cell.base[d] + ((corner >> d) & 1u);
+                row = cell_row<D>(p, gridtype, align_corners, g);
+            } else {
+                row = cr.row(corner);
+            }
             TA *dst = gt + (size_t)row * C;
             if constexpr (C % 2 == 0) {
 #pragma unroll
-                for (uint32_t c = 0; c < C; c += 2) atomic_add_pair<TA>(dst + c, acc[c], acc[c + 1]);
+                for (uint32_t c = 0; c < C; c += 2) atomic_add_pair<TA>(dst + c, acc[corner][c], acc[corner][c + 1]);
             } else {
 #pragma unroll
-                for (uint32_t c = 0; c < C; ++c) atomic_add_one(dst + c, acc[c]);
+                for (uint32_t c = 0; c < C; ++c) atomic_add_one(dst + c, acc[corner][c]);
             }
         }
     }

@@ -136,6 +136,8 @@ struct MarchConst {
     const uint8_t *grid;
     float bound, dt_gamma, dt_min, dt_max, rH;
     float Cf, Hf;
+    float dt_const;     // the step when dt_gamma == 0 (every step is clamp(0, dt_min, dt_max))
+    bool const_step;    // compile-time constant in the <kConstStep = true> kernels
     uint32_t C, H, H3;
 };
 
@@ -144,14 +146,16 @@ struct RayGeo {
 };
 
 __device__ __forceinline__ MarchConst make_const(const uint8_t *grid, float bound, float dt_gamma,
-                                                 uint32_t max_steps, uint32_t C, uint32_t H) {
+                                                 uint32_t max_steps, uint32_t C, uint32_t H, bool const_step = false) {
     MarchConst k;
+    k.const_step = const_step;
     k.grid = grid;
     k.bound = bound;
     k.dt_gamma = dt_gamma;
     const float two_sqrt3 = 2 * 1.7320508075688772f;
     k.dt_min = two_sqrt3 / max_steps;                // raymarching.cu:369
     k.dt_max = two_sqrt3 * (1 << (C - 1)) / H;       // raymarching.cu:370
+    k.dt_const = clampf(0.0f, k.dt_min, k.dt_max);
     k.rH = 1 / (float)H;
     k.Cf = (float)C;
     k.Hf = (float)H;
@@ -169,7 +173,11 @@ __device__ __forceinline__ RayGeo load_ray(const float *__restrict__ o, const fl
     return r;
 }
 
+// dt_gamma == 0 (the LiDAR configurations): t * 0 is +0 for every finite t and NaN otherwise, and fmaxf drops the NaN,
+// so the clamp yields the same constant for every t - the 31-step candidate chain of a window shrinks from
+// (FMUL, FMNMX, FMNMX, FADD) to one FADD per step, bit-identical.
 __device__ __forceinline__ float step_len(const MarchConst &k, float t) {
+    if (k.const_step) return k.dt_const;
     return clampf(t * k.dt_gamma, k.dt_min, k.dt_max);
 }
 
@@ -346,16 +354,17 @@ struct SampleWriter {
 };
 
 // raymarching.cu:332-534 (training march).  One warp per ray.
+template <bool kConstStep>
 __global__ void __launch_bounds__(kThreads)
 k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d,
               const uint8_t *__restrict__ grid, float bound, float dt_gamma, uint32_t max_steps,
               uint32_t N, uint32_t C, uint32_t H, uint32_t M, const float *__restrict__ nears,
               const float *__restrict__ fars, float *__restrict__ xyzs, float *__restrict__ dirs,
               float *__restrict__ deltas, int32_t *__restrict__ rays, int32_t *counter,
-              const float *__restrict__ noises, int32_t *__restrict__ ray_ids) {
+              const float *__restrict__ noises, int32_t *__restrict__ ray_ids, bool zero_tail) {
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
-    const MarchConst k = make_const(grid, bound, dt_gamma, max_steps, C, H);
+    const MarchConst k = make_const(grid, bound, dt_gamma, max_steps, C, H, kConstStep);
     const RayGeo r = load_ray(rays_o + (size_t)n * 3, rays_d + (size_t)n * 3);
     const float far = fars[n];
     float t0 = nears[n];
@@ -363,15 +372,34 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
 
     const uint32_t count = march_warp<false>(k, r, t0, far, max_steps, NoEmit());
 
-    uint32_t offset = 0;
+    uint32_t offset = 0, slot = 0;
     if (lane_id() == 0) {
         offset = (uint32_t)atomicAdd(counter, (int)count);
-        const uint32_t slot = (uint32_t)atomicAdd(counter + 1, 1);
+        if (zero_tail) __threadfence();   // the sample reservation is visible before the ray is counted (see below)
+        slot = (uint32_t)atomicAdd(counter + 1, 1);
         rays[slot * 3] = (int32_t)n;
         rays[slot * 3 + 1] = (int32_t)offset;
         rays[slot * 3 + 2] = (int32_t)count;
     }
     offset = __shfl_sync(kFullMask, offset, 0);
+    if (zero_tail) {
+        // Extended entry point: the warp that takes the LAST ray slot sees the final sample total (every other warp
+        // reserved its samples before it took its slot) and zeroes the rows between the total and the next 128-row
+        // tile boundary - the padding the per-sample kernels process (raymarching.py:235-237 zero-fills the whole
+        // buffers on the host before every call instead).  Nobody else writes those rows.
+        slot = __shfl_sync(kFullMask, slot, 0);
+        if (slot == N - 1) {
+            __threadfence();
+            const uint32_t total = (uint32_t)max(*(volatile int32_t *)counter, 0);
+            const uint32_t hi = min((total + 127u) & ~127u, M);
+            for (uint32_t i = min(total, M) + lane_id(); i < hi; i += 32) {
+                xyzs[(size_t)i * 3] = xyzs[(size_t)i * 3 + 1] = xyzs[(size_t)i * 3 + 2] = 0.f;
+                if (dirs) dirs[(size_t)i * 3] = dirs[(size_t)i * 3 + 1] = dirs[(size_t)i * 3 + 2] = 0.f;
+                if (ray_ids) ray_ids[i] = 0;
+                reinterpret_cast<float2 *>(deltas)[i] = make_float2(0.f, 0.f);
+            }
+        }
+    }
     if (count == 0 || offset + count > M) return;
 
     SampleWriter w{xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
@@ -380,6 +408,7 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
 }
 
 // raymarching.cu:809-928 (inference march: up to n_step samples for each alive ray).
+template <bool kConstStep>
 __global__ void __launch_bounds__(kThreads)
 k_march_infer(uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ rays_alive,
               const float *__restrict__ rays_t, const float *__restrict__ rays_o,
@@ -391,7 +420,7 @@ k_march_infer(uint32_t n_alive, uint32_t n_step, const int32_t *__restrict__ ray
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= n_alive) return;
     const int32_t index = rays_alive[n];
-    const MarchConst k = make_const(grid, bound, dt_gamma, max_steps, C, H);
+    const MarchConst k = make_const(grid, bound, dt_gamma, max_steps, C, H, kConstStep);
     const RayGeo r = load_ray(rays_o + (size_t)index * 3, rays_d + (size_t)index * 3);
     float t = rays_t[index];
     const float far = fars[index];
@@ -562,6 +591,167 @@ k_composite_train_bwd(const float *__restrict__ g_ws, const float *__restrict__ 
     }
 }
 
+// Fused LiDAR compositing step of the training engine: composite forward (raymarching.cu:578-655) -> LiDAR loss and
+// its per-ray gradients (nerf/utils.py:726-734: L1 depth, MSE ray-drop, MSE intensity) -> composite backward
+// (raymarching.cu:691-772 + the depth term).  The warp that owns a ray keeps its forward results in registers and
+// walks the ray's samples a second time for the backward pass (the re-read hits L1/L2), so the per-ray outputs and
+// their gradients never make a round trip through global memory, and every sample of the ray gets a gradient
+// written - zero after the early stop - which removes the zero-fill of the two gradient buffers from the step.
+// Same arithmetic, in the same order, as k_composite_train_fwd + k_lidar_loss + k_composite_train_bwd<2, true>.
+__global__ void __launch_bounds__(kThreads)
+k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
+                       const float *__restrict__ deltas, const int32_t *__restrict__ rays,
+                       const float *__restrict__ gt, const float *__restrict__ nears,
+                       const float *__restrict__ noises, float dt_gamma, float dt_min, float dt_max,
+                       const int32_t *__restrict__ counter, uint32_t M, uint32_t N, float T_thresh, float a_d,
+                       float a_r, float a_i, float loss_scale, float *__restrict__ weights_sum,
+                       float *__restrict__ depth, float *__restrict__ image, float *__restrict__ t0_out,
+                       float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
+                       float *__restrict__ loss_out) {
+    constexpr int NCH = 2;
+    const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (n >= N) return;
+    const unsigned lane = lane_id();
+    if (n == 0 && counter) {
+        // rows between the produced count and the next 128-row tile boundary are processed by the per-sample
+        // kernels but belong to no ray: their gradients are zero
+        const uint32_t cnt = (uint32_t)max(*counter, 0);
+        const uint32_t lo = min(cnt, M), hi = min((cnt + 127u) & ~127u, M);
+        for (uint32_t s = lo + lane; s < hi; s += 32) {
+            grad_sigmas[s] = 0.f;
+            grad_rgbs[(size_t)s * NCH] = 0.f;
+            grad_rgbs[(size_t)s * NCH + 1] = 0.f;
+        }
+    }
+    const uint32_t index = (uint32_t)rays[n * 3];
+    const uint32_t offset = (uint32_t)rays[n * 3 + 1];
+    const uint32_t count = (uint32_t)rays[n * 3 + 2];
+    const bool marched = count != 0 && offset + count <= M;
+
+    // ---------------- forward ----------------
+    float c_final[NCH] = {0.f, 0.f};
+    float ws_final = 0.f, d_final = 0.f;
+    if (marched) {
+        float T_in = 1.0f, t_in = 0.f;
+        for (uint32_t base = 0; base < count; base += 32) {
+            const uint32_t i = base + lane;
+            const bool valid = i < count;
+            const size_t s = (size_t)offset + i;
+            float alpha = 0.f, d_real = 0.f;
+            if (valid) {
+                const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
+                alpha = 1.0f - __expf(-__ldg(sigmas + s) * dl.x);
+                d_real = dl.y;
+            }
+            const float keep = 1.0f - alpha;
+            const float P = warp_scan_mul(keep);
+            float Pex = __shfl_up_sync(kFullMask, P, 1);
+            if (lane == 0) Pex = 1.0f;
+            const float T_before = T_in * Pex;
+            const float T_after = T_before * keep;
+            const float t_here = t_in + warp_scan_add(d_real);
+            const unsigned stop = __ballot_sync(kFullMask, valid && (T_after < T_thresh));
+            const bool use = valid && (stop == 0 || lane < (unsigned)__ffs(stop));
+            if (use) {
+                const float w = alpha * T_before;
+                const float2 col = __ldg(reinterpret_cast<const float2 *>(rgbs) + s);
+                c_final[0] += w * col.x;
+                c_final[1] += w * col.y;
+                d_final += w * t_here;
+                ws_final += w;
+            }
+            if (stop) break;
+            T_in = __shfl_sync(kFullMask, T_after, 31);
+            t_in = __shfl_sync(kFullMask, t_here, 31);
+        }
+        ws_final = warp_sum(ws_final);
+        d_final = warp_sum(d_final);
+        c_final[0] = warp_sum(c_final[0]);
+        c_final[1] = warp_sum(c_final[1]);
+    }
+
+    // ---------------- loss and per-ray gradients (every lane computes the same values) ----------------
+    const float near = __ldg(nears + index);
+    const float start = fmaf(clampf(near * dt_gamma, dt_min, dt_max), __ldg(noises + index), near);   // raymarching.cu:375
+    const float m = __ldg(gt + (size_t)index * 3);
+    const float gti = __ldg(gt + (size_t)index * 3 + 1) * m, gtd = __ldg(gt + (size_t)index * 3 + 2) * m;
+    const float D = d_final + start * ws_final;
+    const float e_d = D * m - gtd;
+    const float e_r = c_final[0] - m;
+    const float e_i = c_final[1] * m - gti;
+    const float inv_n = 1.f / (float)N;
+    const float sc = loss_scale * inv_n;
+    const float gd = a_d * m * (e_d > 0.f ? 1.f : (e_d < 0.f ? -1.f : 0.f)) * sc;
+    const float gw = gd * start;
+    const float gi[NCH] = {2.f * a_r * e_r * sc, 2.f * a_i * e_i * m * sc};
+    if (lane == 0) {
+        weights_sum[index] = ws_final;
+        depth[index] = d_final;
+        reinterpret_cast<float2 *>(image)[index] = make_float2(c_final[0], c_final[1]);
+        if (t0_out) t0_out[index] = start;
+        const float l = (a_d * fabsf(e_d) + a_r * e_r * e_r + a_i * e_i * e_i) * inv_n;
+        if (l != 0.f) atomicAdd(loss_out, l);
+    }
+    if (!marched) return;
+
+    // ---------------- backward ----------------
+    float c_in[NCH] = {0.f, 0.f};
+    float d_in = 0.f, T_in = 1.0f, t_in = 0.f;
+    uint32_t done = count;     // first sample index that received no gradient (early stop)
+    for (uint32_t base = 0; base < count; base += 32) {
+        const uint32_t i = base + lane;
+        const bool valid = i < count;
+        const size_t s = (size_t)offset + i;
+        float alpha = 0.f, d_rgb = 0.f, d_real = 0.f;
+        float2 col = make_float2(0.f, 0.f);
+        if (valid) {
+            const float2 dl = __ldg(reinterpret_cast<const float2 *>(deltas) + s);
+            d_rgb = dl.x;
+            d_real = dl.y;
+            alpha = 1.0f - __expf(-__ldg(sigmas + s) * d_rgb);
+            col = __ldg(reinterpret_cast<const float2 *>(rgbs) + s);
+        }
+        const float keep = 1.0f - alpha;
+        const float P = warp_scan_mul(keep);
+        float Pex = __shfl_up_sync(kFullMask, P, 1);
+        if (lane == 0) Pex = 1.0f;
+        const float T_before = T_in * Pex;
+        const float T_after = T_before * keep;
+        const float w = alpha * T_before;
+        const unsigned stop = __ballot_sync(kFullMask, valid && (T_after < T_thresh));
+        const bool use = valid && (stop == 0 || lane < (unsigned)__ffs(stop));
+
+        float acc = 0.f;
+        float c_run[NCH];
+        c_run[0] = c_in[0] + warp_scan_add(w * col.x);
+        acc += gi[0] * (T_after * col.x - (c_final[0] - c_run[0]));
+        c_run[1] = c_in[1] + warp_scan_add(w * col.y);
+        acc += gi[1] * (T_after * col.y - (c_final[1] - c_run[1]));
+        acc += gw * (1 - ws_final);
+        const float t_here = t_in + warp_scan_add(d_real);
+        const float d_run = d_in + warp_scan_add(w * t_here);
+        acc += gd * (T_after * t_here - (d_final - d_run));
+        if (valid) {
+            reinterpret_cast<float2 *>(grad_rgbs)[s] = use ? make_float2(gi[0] * w, gi[1] * w) : make_float2(0.f, 0.f);
+            grad_sigmas[s] = use ? d_rgb * acc : 0.f;
+        }
+        if (stop) {
+            done = base + 32;
+            break;
+        }
+        T_in = __shfl_sync(kFullMask, T_after, 31);
+        c_in[0] = __shfl_sync(kFullMask, c_run[0], 31);
+        c_in[1] = __shfl_sync(kFullMask, c_run[1], 31);
+        t_in = __shfl_sync(kFullMask, t_here, 31);
+        d_in = __shfl_sync(kFullMask, d_run, 31);
+    }
+    for (uint32_t i = done + lane; i < count; i += 32) {   // samples behind the early stop (raymarching.py:338-339)
+        const size_t s = (size_t)offset + i;
+        reinterpret_cast<float2 *>(grad_rgbs)[s] = make_float2(0.f, 0.f);
+        grad_sigmas[s] = 0.f;
+    }
+}
+
 // raymarching.cu:967-1053 (inference compositing).  n_step is small (<= 8 in the upstream
 // driver), so one thread per ray is the right granularity; T = 1 - weight_sum (not a product).
 __global__ void __launch_bounds__(kThreads)
@@ -682,20 +872,30 @@ int lnb_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *b
     return launch_status();
 }
 
+static int march_rays_train_impl(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
+                                 float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
+                                 uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
+                                 float *deltas, int32_t *rays, int32_t *counter, const float *noises,
+                                 int32_t *ray_ids, int zero_tail, lnb_stream_t stream) {
+    LNB_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises);
+    LNB_REQUIRE(M == 0 || (xyzs && deltas && (dirs || ray_ids)));
+    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024 && max_steps >= 1);
+    if (N == 0) return LNB_OK;
+    auto kern = (dt_gamma == 0.0f) ? k_march_train<true> : k_march_train<false>;
+    kern<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
+        rays, counter, noises, ray_ids, zero_tail != 0);
+    count_launch();
+    return launch_status();
+}
+
 int lnb_march_rays_train_ex(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
                             float dt_gamma, uint32_t max_steps, uint32_t N, uint32_t C, uint32_t H,
                             uint32_t M, const float *nears, const float *fars, float *xyzs, float *dirs,
                             float *deltas, int32_t *rays, int32_t *counter, const float *noises,
                             int32_t *ray_ids, lnb_stream_t stream) {
-    LNB_REQUIRE(rays_o && rays_d && grid && nears && fars && rays && counter && noises);
-    LNB_REQUIRE(M == 0 || (xyzs && deltas && (dirs || ray_ids)));
-    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024 && max_steps >= 1);
-    if (N == 0) return LNB_OK;
-    k_march_train<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
-        rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs, deltas,
-        rays, counter, noises, ray_ids);
-    count_launch();
-    return launch_status();
+    return march_rays_train_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                                 deltas, rays, counter, noises, ray_ids, 1, stream);
 }
 
 int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t *grid, float bound,
@@ -704,8 +904,8 @@ int lnb_march_rays_train(const float *rays_o, const float *rays_d, const uint8_t
                          float *deltas, int32_t *rays, int32_t *counter, const float *noises,
                          lnb_stream_t stream) {
     LNB_REQUIRE(M == 0 || dirs);
-    return lnb_march_rays_train_ex(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs,
-                                   dirs, deltas, rays, counter, noises, nullptr, stream);
+    return march_rays_train_impl(rays_o, rays_d, grid, bound, dt_gamma, max_steps, N, C, H, M, nears, fars, xyzs, dirs,
+                                 deltas, rays, counter, noises, nullptr, 0, stream);
 }
 
 int lnb_composite_rays_train_forward_ex(const float *sigmas, const float *rgbs, const float *deltas,
@@ -788,6 +988,26 @@ int lnb_composite_rays_train_backward(const float *grad_weights_sum, const float
                                                 T_thresh, 3, grad_sigmas, grad_rgbs, stream);
 }
 
+int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                              const float *gt, const float *nears, const float *noises, float dt_gamma,
+                              uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
+                              uint32_t N, float T_thresh, float alpha_d, float alpha_r, float alpha_i,
+                              float loss_scale, float *weights_sum, float *depth, float *image, float *t0,
+                              float *grad_sigmas, float *grad_rgbs, float *loss_out, lnb_stream_t stream) {
+    LNB_REQUIRE(rays && gt && nears && noises && weights_sum && depth && image && loss_out);
+    LNB_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs));
+    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && max_steps >= 1);
+    if (N == 0) return LNB_OK;
+    const float two_sqrt3 = 2 * 1.7320508075688772f;       // same expressions as make_const()
+    const float dt_min = two_sqrt3 / max_steps;
+    const float dt_max = two_sqrt3 * (1 << (C - 1)) / H;
+    k_lidar_composite_step<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, gt, nears, noises, dt_gamma, dt_min, dt_max, counter, M, N, T_thresh, alpha_d,
+        alpha_r, alpha_i, loss_scale, weights_sum, depth, image, t0, grad_sigmas, grad_rgbs, loss_out);
+    count_launch();
+    return launch_status();
+}
+
 int lnb_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive, const float *rays_t,
                    const float *rays_o, const float *rays_d, float bound, float dt_gamma,
                    uint32_t max_steps, uint32_t C, uint32_t H, const uint8_t *grid,
@@ -797,10 +1017,10 @@ int lnb_march_rays(uint32_t n_alive, uint32_t n_step, const int32_t *rays_alive,
     LNB_REQUIRE(xyzs && dirs && deltas);
     LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && H <= 1024 && max_steps >= 1);
     if (n_alive == 0 || n_step == 0) return LNB_OK;
-    k_march_infer<<<blocks_for_threads((uint64_t)n_alive * 32, kThreads), kThreads, 0,
-                    as_stream(stream)>>>(n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound,
-                                         dt_gamma, max_steps, C, H, grid, nears, fars, xyzs, dirs,
-                                         deltas, noises);
+    auto kern = (dt_gamma == 0.0f) ? k_march_infer<true> : k_march_infer<false>;
+    kern<<<blocks_for_threads((uint64_t)n_alive * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        n_alive, n_step, rays_alive, rays_t, rays_o, rays_d, bound, dt_gamma, max_steps, C, H, grid, nears, fars,
+        xyzs, dirs, deltas, noises);
     count_launch();
     return launch_status();
 }

@@ -60,6 +60,7 @@ class FieldConfig:
     grid_update_interval: int = 16
     perturb: bool = True                 # jitter the march start (Trainer.train_step passes perturb=True)
     fused_field: bool = True             # density MLP + LiDAR head as the fused field kernels (csrc/field.cu)
+    fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
     seed: int = 0
 
     @property
@@ -163,6 +164,7 @@ class LidarFieldEngine:
 
         self.M = 0
         self._graph = None
+        self._side = torch.cuda.Stream(device=dev)     # side branch of the step (per-ray direction terms)
         self._alloc_samples(sample_budget or N * 64)
 
     # ------------------------------------------------------------------------------------------------------
@@ -209,9 +211,18 @@ class LidarFieldEngine:
             self.noises.uniform_(0, 1)
         else:
             self.noises.zero_()
-        # march start per ray, for the absolute-depth term of the loss (raymarching.cu:375)
-        torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
-        torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
+        if not c.fused_composite:
+            # march start per ray, for the absolute-depth term of the loss (raymarching.cu:375)
+            torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
+            torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
+        if self.fused:
+            # per-ray direction terms depend only on rays_d and the head weights: a side branch next to the march
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
+                                            u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
+                    "ray_terms")
 
         _ck(lib.lnb_march_rays_train_ex(p(self.rays_o), p(self.rays_d), p(self.bitfield), f32(c.bound), f32(c.dt_gamma),
                                         u32(c.max_steps), u32(N), u32(c.cascade), u32(c.grid_size), u32(M),
@@ -220,16 +231,14 @@ class LidarFieldEngine:
                                         p(self.counter), p(self.noises), p(self.ray_ids), s), "march_rays_train")
         # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
+        # (the extended march also zeroes the padding rows of the last tile)
         na = p(self.counter)
-        _ck(lib.lnb_zero_sample_tail_ex(p(self.xyzs), p(self.dirs) if self.dirs is not None else vp(0), p(self.deltas),
-                                        p(self.ray_ids), na, u32(M), s), "zero_tail")
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
             "grid_fwd")
         if self.fused:
-            _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
-                                        u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), s), "ray_terms")
+            torch.cuda.current_stream().wait_stream(self._side)        # join: ray terms ready
             _ck(lib.lnb_field_forward(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
                                       p(self.ray_bias), u32(M), u32(self.enc_dim), u32(c.sigma_layers),
                                       u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim),
@@ -246,17 +255,25 @@ class LidarFieldEngine:
                                          u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), p(self.fb_head),
                                          p(self.head_out), na, s), "ffmlp_fwd(head)")
             _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), na, s), "head_rgb")
-        rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2, self.ws,
-                                           self.depth, self.image)
-        _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N), f32(c.alpha_d),
-                               f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale), p(self.g_ws), p(self.g_depth),
-                               p(self.g_image), p(self.loss_acc), s), "lidar_loss")
-        # ---- backward ----
-        self.g_sigma.zero_()
-        self.g_rgb.zero_()
-        rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb, self.deltas,
-                                            self.rays, self.ws, self.depth, self.image, M, N, c.T_thresh, 2,
-                                            self.g_sigma, self.g_rgb)
+        if c.fused_composite:
+            _ck(lib.lnb_lidar_composite_step(p(self.sigma), p(self.rgb), p(self.deltas), p(self.rays), p(self.gt),
+                                             p(self.nears), p(self.noises), f32(c.dt_gamma), u32(c.max_steps),
+                                             u32(c.cascade), u32(c.grid_size), na, u32(M), u32(N), f32(c.T_thresh),
+                                             f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale),
+                                             p(self.ws), p(self.depth), p(self.image), p(self.t0), p(self.g_sigma),
+                                             p(self.g_rgb), p(self.loss_acc), s), "lidar_composite_step")
+        else:
+            rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2,
+                                               self.ws, self.depth, self.image)
+            _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N),
+                                   f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale), p(self.g_ws),
+                                   p(self.g_depth), p(self.g_image), p(self.loss_acc), s), "lidar_loss")
+            # ---- backward ----
+            self.g_sigma.zero_()
+            self.g_rgb.zero_()
+            rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb,
+                                                self.deltas, self.rays, self.ws, self.depth, self.image, M, N,
+                                                c.T_thresh, 2, self.g_sigma, self.g_rgb)
         if self.fused:
             _ck(lib.lnb_field_head_backward(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                             p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),

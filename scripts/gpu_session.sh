@@ -5,16 +5,28 @@
 set -u
 OUT=gpurun_out
 mkdir -p $OUT
-WHAT="${*:-tests bench ref launches full}"
+WHAT="${*:-micro tests bench ref launches full}"
 has() { [[ " $WHAT " == *" $1 "* ]]; }
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > $OUT/gpu.txt 2>&1
 
+if has micro; then
+  ./scripts/micro/mma_shapes.bin > $OUT/mma_shapes.txt 2>&1
+  cat $OUT/mma_shapes.txt
+fi
 if has tests; then
   ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
   echo "pytest exit $?" >> $OUT/pytest_gpu.log
   tail -5 $OUT/pytest_gpu.log
   ( time timeout 300 python -c "import __graft_entry__ as g; g.smoke()" ) > $OUT/smoke.log 2>&1
   tail -3 $OUT/smoke.log
+fi
+if has trace; then
+  LNB200_LIB=lidar-nerf_b200/lib/liblnb200_trace.so timeout 300 python scripts/diag_bwd_trace.py > $OUT/bwd_trace.txt 2>&1
+  tail -2 $OUT/bwd_trace.txt
+fi
+if has overlap; then
+  timeout 300 python scripts/diag_overlap.py > $OUT/overlap.txt 2>&1
+  tail -25 $OUT/overlap.txt
 fi
 if has bench; then
   ( time timeout 600 python bench.py ) > $OUT/bench.log 2> $OUT/bench.err

@@ -34,6 +34,43 @@ def test_unfused_chain_matches_cpu_restatement_and_fused_kernels():
         assert (ids[off:off + cnt] == n).all()
 
 
+def test_fused_composite_step_equals_the_three_kernel_chain():
+    """lnb_lidar_composite_step = composite forward + lidar_loss + composite backward (+ the zero fill it removes)."""
+    from oracle import check_engine
+    res = {}
+    for fused in (False, True):
+        cfg = check_engine.small_config(perturb=False, fused_composite=fused, T_thresh=1e-2, density_scale=50.0)
+        eng, gpu, _ = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg)
+        n = gpu["n_samples"]
+        rows = (n + 127) // 128 * 128
+        # sample rows in ray order (the march hands out offsets in arrival order, which differs between runs)
+        rays = eng.rays.cpu().numpy()
+        rays = rays[np.argsort(rays[:, 0])]
+        order = np.concatenate([np.arange(o, o + k) for _, o, k in rays])
+        assert len(order) == n
+        res[fused] = dict(gpu=gpu, g_sigma=eng.g_sigma.cpu().numpy()[order], g_rgb=eng.g_rgb.cpu().numpy()[order],
+                          tail=eng.g_sigma[n:rows].cpu().numpy(), t0=eng.t0.cpu().numpy())
+        if fused:
+            # poison the gradient buffers: the fused kernel must overwrite every row the later kernels read
+            eng.g_sigma.fill_(float("nan"))
+            eng.g_rgb.fill_(float("nan"))
+            eng.G.zero_()
+            eng._forward_backward()
+            torch.cuda.synchronize()
+            assert torch.isfinite(eng.g_sigma[:rows]).all() and torch.isfinite(eng.g_rgb[:rows]).all()
+            assert torch.isfinite(eng.G).all()
+    a, b = res[True], res[False]
+    assert (b["g_sigma"] == 0).mean() > 0.05, "the case must exercise the early stop"
+    np.testing.assert_array_equal(a["gpu"]["counts"], b["gpu"]["counts"])
+    for k in ("ws", "depth", "image"):
+        np.testing.assert_allclose(a["gpu"][k], b["gpu"][k], rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(a["t0"], b["t0"], rtol=1e-6)
+    assert (a["tail"] == 0).all()
+    np.testing.assert_allclose(a["g_sigma"], b["g_sigma"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(a["g_rgb"], b["g_rgb"], rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(a["gpu"]["loss"], b["gpu"]["loss"], rtol=1e-5)
+
+
 def test_fused_step_full_size_table_matches_cpu_restatement():
     from oracle import check_engine
     cfg = check_engine.small_config(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
