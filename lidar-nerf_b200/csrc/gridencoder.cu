@@ -239,6 +239,9 @@ __device__ __forceinline__ void interp_corners(const Cell<D> &cell, const LevelG
     // all gathers first (2^D independent loads in flight, kept in the table's type), then the rounding-ordered
     // accumulation
     __align__(16) T v[1u << D][C];
+    // (Loading the two x-neighbours of a hashed level as ONE aligned 8-byte pair when the base x is even - they differ
+    // only in bit 0 of the xor - was measured on B200: 115 -> 125 us.  The extra selects and the divergent second path
+    // cost more than the saved L1 lookups; the gather is not lookup-bound.)
 #pragma unroll
     for (uint32_t corner = 0; corner < (1u << D); ++corner) {
         uint32_t row;
@@ -266,9 +269,9 @@ __device__ __forceinline__ void interp_corners(const Cell<D> &cell, const LevelG
     }
 }
 
-// Forward.
-template <typename T, uint32_t D, uint32_t C>
-__global__ void __launch_bounds__(kFwdThreads, 3)
+// Forward.  kMinBlocks = resident CTAs per SM the register allocation is sized for (3: 40 registers, 2: 64).
+template <typename T, uint32_t D, uint32_t C, int kMinBlocks = 3>
+__global__ void __launch_bounds__(kFwdThreads, kMinBlocks)
 k_grid_fwd(const float *__restrict__ inputs, const T *__restrict__ table,
            const int32_t *__restrict__ offsets, T *__restrict__ outputs, uint32_t B, uint32_t L,
            float S, uint32_t H, T *__restrict__ dy_dx, uint32_t gridtype, bool align_corners,
@@ -614,6 +617,10 @@ int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *
                             ? (size_t)kTileB * (F + (sizeof(T) == 2 ? 2 : 1)) * sizeof(T) : 0;
     if (smem > 200 * 1024) return LNB_ERR_UNSUPPORTED;
     auto kern = k_grid_fwd<T, D, C>;
+    if constexpr (sizeof(T) == 2 && D == 3 && C == 2) {
+        static const int occ = [] { const char *e = getenv("LNB_GRID_FWD_OCC"); return e ? atoi(e) : 3; }();
+        if (occ == 2) kern = k_grid_fwd<T, D, C, 2>;
+    }
     if (smem > 48 * 1024)
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const unsigned threads = (L >= 16) ? kFwdThreads : max(32u, min((unsigned)kFwdThreads, L * 32u));

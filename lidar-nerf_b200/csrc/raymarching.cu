@@ -226,9 +226,19 @@ __device__ __forceinline__ Cand probe(const MarchConst &k, const RayGeo &r, floa
 // Marches one ray with the whole warp.  `emit(rank, cand, delta_real)` is called by the lane that
 // owns emitted sample number `rank` (0-based along the ray).  Returns the number of samples
 // (<= cap).  All lanes must call with identical arguments.
+// What the counting pass remembers for the emitting pass: the windows that emitted anything, as (emit mask, t of the
+// window's first candidate), window i held by lane i.  The candidate sequence does not depend on the grid, so the
+// second pass only has to rebuild t inside those windows - no occupancy probes, no skip resolution, and windows that
+// lie entirely in empty space are not visited at all.
+struct WindowLog {
+    unsigned mask = 0;        // this lane's window: which candidates were emitted
+    float base = 0.f;         // this lane's window: t of candidate 0
+    uint32_t n = 0;           // windows logged (uniform); > 32 = overflow, the caller re-marches instead
+};
+
 template <bool kEmit, class Emit>
 __device__ __forceinline__ uint32_t march_warp(const MarchConst &k, const RayGeo &r, float t_start,
-                                               float far, uint32_t cap, Emit emit) {
+                                               float far, uint32_t cap, Emit emit, WindowLog *log = nullptr) {
     if (cap == 0) return 0;
     const unsigned lane = lane_id();
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -313,6 +323,13 @@ __device__ __forceinline__ uint32_t march_warp(const MarchConst &k, const RayGeo
             }
         }
 
+        if (log && emit_mask) {
+            if (lane == log->n) {
+                log->mask = emit_mask;
+                log->base = base_t;
+            }
+            ++log->n;
+        }
         if (kEmit) {
             const float t_after = t + c.dt;
             const unsigned before = emit_mask & lt_mask;
@@ -329,6 +346,40 @@ __device__ __forceinline__ uint32_t march_warp(const MarchConst &k, const RayGeo
         base_t = next_base;
     }
     return emitted;
+}
+
+// Second pass from a WindowLog: same samples, same bits as march_warp<true> (t is rebuilt by the same serial adds,
+// position / step / delta by the same expressions as probe()).
+template <class Emit>
+__device__ __forceinline__ void replay_windows(const MarchConst &k, const RayGeo &r, float t_start, const WindowLog &log,
+                                               Emit emit) {
+    const unsigned lane = lane_id();
+    const unsigned lt_mask = (1u << lane) - 1u;
+    float last_t = t_start;
+    uint32_t emitted = 0;
+    for (uint32_t w = 0; w < log.n; ++w) {
+        const unsigned emit_mask = __shfl_sync(kFullMask, log.mask, w);
+        float t = __shfl_sync(kFullMask, log.base, w);
+#pragma unroll
+        for (int i = 0; i < 31; ++i) {
+            const float tn = t + step_len(k, t);
+            if ((unsigned)i < lane) t = tn;
+        }
+        Cand c;
+        c.x = clampf(r.ox + t * r.dx, -k.bound, k.bound);
+        c.y = clampf(r.oy + t * r.dy, -k.bound, k.bound);
+        c.z = clampf(r.oz + t * r.dz, -k.bound, k.bound);
+        c.dt = step_len(k, t);
+        c.tt = 0.f;
+        c.occ = true;
+        const float t_after = t + c.dt;
+        const unsigned before = emit_mask & lt_mask;
+        const int prev_lane = before ? (31 - __clz(before)) : 0;
+        const float prev_after = __shfl_sync(kFullMask, t_after, prev_lane);
+        if ((emit_mask >> lane) & 1u) emit(emitted + __popc(before), c, t_after - (before ? prev_after : last_t));
+        last_t = __shfl_sync(kFullMask, t_after, 31 - __clz(emit_mask));
+        emitted += __popc(emit_mask);
+    }
 }
 
 struct NoEmit {
@@ -370,7 +421,8 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
     float t0 = nears[n];
     t0 += step_len(k, t0) * noises[n];  // raymarching.cu:375
 
-    const uint32_t count = march_warp<false>(k, r, t0, far, max_steps, NoEmit());
+    WindowLog log;
+    const uint32_t count = march_warp<false>(k, r, t0, far, max_steps, NoEmit(), &log);
 
     uint32_t offset = 0, slot = 0;
     if (lane_id() == 0) {
@@ -404,7 +456,8 @@ k_march_train(const float *__restrict__ rays_o, const float *__restrict__ rays_d
 
     SampleWriter w{xyzs + (size_t)offset * 3, dirs ? dirs + (size_t)offset * 3 : nullptr,
                    deltas + (size_t)offset * 2, r.dx, r.dy, r.dz, ray_ids ? ray_ids + offset : nullptr, (int32_t)n};
-    march_warp<true>(k, r, t0, far, count, w);
+    if (log.n <= 32) replay_windows(k, r, t0, log, w);
+    else march_warp<true>(k, r, t0, far, count, w);     // more than 32 non-empty windows: march again
 }
 
 // raymarching.cu:809-928 (inference march: up to n_step samples for each alive ray).

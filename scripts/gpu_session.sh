@@ -46,7 +46,7 @@ fi
 if has full; then
   # the heavy kernels of one steady-state step (eager launches; skip the preparation phase's launches)
   timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_field_fwd|k_mlp_bwd|k_grid_fwd|k_grid_bwd|k_march_train|k_adam|k_composite_train' \
+    -k regex:'k_field_fwd|k_mlp_bwd|k_grid_fwd|k_grid_bwd|k_march_train|k_adam|k_composite_train|k_lidar_composite_step|k_ray_dir_terms' \
     --profile-from-start off -c ${NCU_COUNT:-12} -f -o $OUT/full \
     python bench.py --steps 2 --warmup 3 --no-graph --no-cpu-baseline --no-profile --profiler-range > $OUT/full_bench.log 2>&1
   ls -la $OUT/full.ncu-rep
