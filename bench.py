@@ -193,6 +193,10 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     N = args.rays
     cfg = FieldConfig()
+    if os.environ.get("LNB_COMPACT_BACKWARD") == "0":     # A/B switch for the diagnostics in profiles/
+        cfg.compact_backward = False
+    if os.environ.get("LNB_LATE_GRAD_ZERO") == "0":
+        cfg.late_grad_zero = False
     seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
     eng = LidarFieldEngine(cfg, N, device=dev, sample_budget=N * 64)
     eng.seed_occupancy_from_points(seq.surface_points())
@@ -382,7 +386,8 @@ def profile_kernels(eng, pool, load, iters=5):
                       (E.rm, "composite_rays_train_backward_ex"), (E.ff, "ffmlp_forward")):
         saved.append((obj, name, wrap(obj, name, name)))
     lib_names = ["lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_ray_terms", "lnb_field_forward",
-                 "lnb_field_head_backward", "lnb_lidar_composite_step",
+                 "lnb_field_head_backward", "lnb_lidar_composite_step", "lnb_field_head_backward_rows",
+                 "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
                  "lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_ffmlp_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
                  "lnb_lidar_loss", "lnb_field_head_out_grad", "lnb_ffmlp_backward_accumulate", "lnb_field_sigma_out_grad",
                  "lnb_grid_encode_backward_ex"]
@@ -471,6 +476,10 @@ def profile_kernels(eng, pool, load, iters=5):
         "lnb_ffmlp_forward_ex": (rows * ((64 + 32 + 2 * 128) + (192 + 32 + 2 * 128)) // 2,
                           "per sample inputs + outputs + 2 saved activation rows (avg of both MLPs)"),
     }
+    for a_, b_ in (("lnb_field_head_backward_rows", "lnb_field_head_backward"),
+                   ("lnb_ffmlp_backward_accumulate_rows", "lnb_ffmlp_backward_accumulate"),
+                   ("lnb_grid_encode_backward_rows", "lnb_grid_encode_backward_ex")):
+        alg[a_] = alg[b_]       # same algorithmic work per MARCHED sample; the kernels skip the rows that carry no gradient
     launches = us[top]["launches_per_step"]
     dur_s = us[top]["us_per_step"] / max(launches, 1) * 1e-6
     # DRAM bytes per launch of each kernel from the committed `ncu --set full` capture (profiles/): measured offline

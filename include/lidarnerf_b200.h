@@ -282,13 +282,18 @@ int lnb_lidar_loss(const float *weights_sum, const float *depth, const float *im
  * marched ray receives a gradient (zero behind the early stop) and the rows between counter[0] and the next
  * multiple of 128 are zeroed, so grad_sigmas / grad_rgbs need no zero fill.  The march start of each ray,
  * near + clamp(near * dt_gamma, dt_min, dt_max) * noise (raymarching.cu:369-375), is recomputed from
- * (nears, noises, dt_gamma, max_steps, C, H) and written to t0 [N] (nullable).  loss_out[0] += loss. */
+ * (nears, noises, dt_gamma, max_steps, C, H) and written to t0 [N] (nullable).  loss_out[0] += loss.
+ * live_idx [M] / n_live [1] (both nullable): the rows that can carry a gradient - each ray's samples up to and
+ * including the one that drove T below T_thresh - are appended to live_idx in arrival order and counted in n_live
+ * (the caller zeroes n_live); the *_rows backward entry points below walk that list instead of all marched rows
+ * (25-30 % of the marched samples of a LiDAR scene sit behind the first surface and have an exactly-zero gradient). */
 int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
                               const float *gt, const float *nears, const float *noises, float dt_gamma,
                               uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
                               uint32_t N, float T_thresh, float alpha_d, float alpha_r, float alpha_i,
                               float loss_scale, float *weights_sum, float *depth, float *image, float *t0,
-                              float *grad_sigmas, float *grad_rgbs, float *loss_out, lnb_stream_t stream);
+                              float *grad_sigmas, float *grad_rgbs, float *loss_out, int32_t *live_idx,
+                              int32_t *n_live, lnb_stream_t stream);
 int lnb_field_head_out_grad(const float *g_rgb, const float *rgb, uint32_t M, void *g_head_out,
                             const int32_t *n_active, lnb_stream_t stream);
 int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const void *g_head_in, uint32_t M,
@@ -328,6 +333,28 @@ int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g
                             uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
                             float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
                             lnb_stream_t stream);
+/* Row-compacted backward entry points (the fused step's backward pass on live samples only, see
+ * lnb_lidar_composite_step): row r of the kernel reads its per-row INPUTS (saved activations, layer inputs, sig_out,
+ * g_rgb, rgb, g_sigma, ray_ids, sample coordinates) at row row_idx[r]; the gradients handed from one backward kernel
+ * to the next (g_sig_out, grad_inputs, grid `grad`) are in compact order; n_rows[0] (device) is the exact row count. */
+int lnb_field_head_backward_rows(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                                 const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                                 uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree,
+                                 uint32_t hidden, float density_scale, void *g_sig_out, float *grad_w_head_f32,
+                                 const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream);
+int lnb_ffmlp_backward_accumulate_rows(const void *grad, const void *inputs, const void *weights,
+                                       const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                       uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                       uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
+                                       float *grad_weights_f32, const int32_t *row_idx, const int32_t *n_rows,
+                                       lnb_stream_t stream);
+/* [B, L*C] gradient layout only */
+int lnb_grid_encode_backward_rows(const void *grad, const float *inputs, const void *embeddings,
+                                  const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D,
+                                  uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                  uint32_t interp, int dtype, float in_bound, int accumulate_f32,
+                                  const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream);
+
 
 #ifdef __cplusplus
 }

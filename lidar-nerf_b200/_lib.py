@@ -42,6 +42,7 @@ SYMBOLS = [
     "lnb_field_forward", "lnb_field_head_backward",
     "lnb_zero_sample_tail", "lnb_field_head_input", "lnb_field_head_rgb", "lnb_lidar_loss",
     "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays", "lnb_lidar_composite_step",
+    "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
 ]
 
 

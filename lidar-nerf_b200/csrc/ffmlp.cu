@@ -257,8 +257,10 @@ size_t lnb_ffmlp_backward_workspace_bytes(uint32_t input_dim, uint32_t output_di
 
 static int ffmlp_backward_impl(const void *grad, const void *inputs, const void *weights, const void *forward_buffer,
                                uint32_t B, const Shape &sh, int calc_grad_inputs, void *backward_buffer,
-                               void *grad_inputs, float *wgrad_f32, const int32_t *n_active, cudaStream_t st) {
+                               void *grad_inputs, float *wgrad_f32, const int32_t *n_active, cudaStream_t st,
+                               const int32_t *row_idx = nullptr) {
     BwdArgs a = {};
+    a.row_idx = row_idx;
     a.W = static_cast<const __half *>(weights);
     a.fbuf = static_cast<const __half *>(forward_buffer);
     a.B = B;
@@ -318,6 +320,23 @@ int lnb_ffmlp_backward_accumulate(const void *grad, const void *inputs, const vo
     if (B == 0) return LNB_OK;
     return ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, nullptr, grad_inputs,
                                grad_weights_f32, n_active, as_stream(stream));
+}
+
+int lnb_ffmlp_backward_accumulate_rows(const void *grad, const void *inputs, const void *weights,
+                                       const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                       uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                       uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
+                                       float *grad_weights_f32, const int32_t *row_idx, const int32_t *n_rows,
+                                       lnb_stream_t stream) {
+    if (!grad || !inputs || !weights || !forward_buffer || !grad_weights_f32 || !row_idx || !n_rows)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (calc_grad_inputs && !grad_inputs) return LNB_ERR_INVALID_ARGUMENT;
+    Shape sh;
+    int rc = check_shape(B, input_dim, output_dim, hidden_dim, num_layers, activation, output_activation, &sh);
+    if (rc != LNB_OK) return rc;
+    if (B == 0) return LNB_OK;
+    return ffmlp_backward_impl(grad, inputs, weights, forward_buffer, B, sh, calc_grad_inputs, nullptr, grad_inputs,
+                               grad_weights_f32, n_rows, as_stream(stream), row_idx);
 }
 
 int lnb_allocate_splitk(size_t size) {

@@ -409,11 +409,11 @@ int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, 
     return launch_status();
 }
 
-int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
-                            const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
-                            uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
-                            float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
-                            lnb_stream_t stream) {
+static int field_head_backward_impl(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                                    const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                                    uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree,
+                                    uint32_t hidden, float density_scale, void *g_sig_out, float *grad_w_head_f32,
+                                    const int32_t *n_active, const int32_t *row_idx, lnb_stream_t stream) {
     if (!g_rgb || !rgb || !g_sigma || !sig_out || !ray_ids || !ray_enc || !w_head || !fb_head || !g_sig_out ||
         !grad_w_head_f32)
         return LNB_ERR_INVALID_ARGUMENT;
@@ -429,6 +429,7 @@ int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g
     a.sh = fs.h;
     a.wgrad = grad_w_head_f32;
     a.n_active = n_active;
+    a.row_idx = row_idx;
     a.g_rgb = g_rgb;
     a.rgb = rgb;
     a.g_sigma = g_sigma;
@@ -446,6 +447,27 @@ int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g
     if (rc2 != LNB_OK) return rc2;
     count_launch();
     return launch_status();
+}
+
+int lnb_field_head_backward(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                            const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                            uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                            float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
+                            lnb_stream_t stream) {
+    return field_head_backward_impl(g_rgb, rgb, g_sigma, sig_out, ray_ids, ray_enc, w_head, fb_head, M, head_in_pad,
+                                    head_layers, degree, hidden, density_scale, g_sig_out, grad_w_head_f32, n_active,
+                                    nullptr, stream);
+}
+
+int lnb_field_head_backward_rows(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                                 const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                                 uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree,
+                                 uint32_t hidden, float density_scale, void *g_sig_out, float *grad_w_head_f32,
+                                 const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream) {
+    if (!row_idx || !n_rows) return LNB_ERR_INVALID_ARGUMENT;
+    return field_head_backward_impl(g_rgb, rgb, g_sigma, sig_out, ray_ids, ray_enc, w_head, fb_head, M, head_in_pad,
+                                    head_layers, degree, hidden, density_scale, g_sig_out, grad_w_head_f32, n_rows,
+                                    row_idx, stream);
 }
 
 #ifdef LNB_TRACE

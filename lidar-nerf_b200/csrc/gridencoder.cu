@@ -454,11 +454,18 @@ __global__ void __launch_bounds__(kBwdThreads)
 k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
            const int32_t *__restrict__ offsets, TA *__restrict__ grad_table, uint32_t B, uint32_t L,
            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout, float2 norm,
-           uint32_t n_agg, const int32_t *__restrict__ n_active) {
+           uint32_t n_agg, const int32_t *__restrict__ n_active, const int32_t *__restrict__ row_idx) {
     __shared__ LevelGeo s_geo[kMaxLevelsShared];
     __shared__ LevelIndex<D> s_idx[kMaxLevelsShared];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    const uint32_t Bact = active_rows(B, n_active);
+    // row_idx (nullable): gradient row b belongs to the sample at inputs[row_idx[b]], *n_active is the exact row count
+    uint32_t Bact;
+    if (row_idx) {
+        const int32_t nv = *n_active;
+        Bact = min(B, (uint32_t)(nv > 0 ? nv : 0));
+    } else {
+        Bact = active_rows(B, n_active);
+    }
     if (blockIdx.x * blockDim.x >= Bact) return;
     if (threadIdx.x < min(L, kMaxLevelsShared)) {   // level-uniform quantities, once per CTA
         const LevelGeo g = level_geo(offsets, threadIdx.x, S, H);
@@ -470,7 +477,7 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
 
     float v[D];
     bool inside = false;
-    if (in_range) inside = load_unit_coords<D>(inputs + (size_t)b * D, norm, v);
+    if (in_range) inside = load_unit_coords<D>(inputs + (size_t)(row_idx ? (uint32_t)__ldg(row_idx + b) : b) * D, norm, v);
     else {
 #pragma unroll
         for (uint32_t d = 0; d < D; ++d) v[d] = 0.f;
@@ -634,7 +641,8 @@ int run_fwd(const float *inputs, const void *emb, const int32_t *offsets, void *
 template <typename T, uint32_t D, uint32_t C>
 int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void *grad_emb, uint32_t B,
             uint32_t L, float S, uint32_t H, const void *dy_dx, void *grad_inputs, uint32_t gridtype,
-            bool ac, uint32_t interp, int layout, float2 norm, bool acc_f32, const int32_t *n_active, cudaStream_t st) {
+            bool ac, uint32_t interp, int layout, float2 norm, bool acc_f32, const int32_t *n_active, cudaStream_t st,
+            const int32_t *row_idx = nullptr) {
     // leading (coarse) levels with resolution <= agg_max_res use the run-aggregating variant
     uint32_t n_agg = 0;
     {
@@ -649,11 +657,11 @@ int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void 
     if (acc_f32 && sizeof(T) == 2)
         k_grid_bwd<T, float, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
                                                                static_cast<float *>(grad_emb), B, L, S, H, gridtype,
-                                                               ac, interp, layout, norm, n_agg, n_active);
+                                                               ac, interp, layout, norm, n_agg, n_active, row_idx);
     else
         k_grid_bwd<T, T, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
                                                            static_cast<T *>(grad_emb), B, L, S, H, gridtype, ac,
-                                                           interp, layout, norm, n_agg, n_active);
+                                                           interp, layout, norm, n_agg, n_active, row_idx);
     count_launch();
     int rc = launch_status();
     if (rc != LNB_OK) return rc;
@@ -759,6 +767,26 @@ int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const voi
     const bool acc32 = accumulate_f32 != 0;
     LNB_GRID_DISPATCH(run_bwd, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs,
                       gridtype, ac, interp, layout, norm, acc32, n_active, st);
+}
+
+int lnb_grid_encode_backward_rows(const void *grad, const float *inputs, const void *embeddings,
+                                  const int32_t *offsets, void *grad_embeddings, uint32_t B, uint32_t D,
+                                  uint32_t C, uint32_t L, float S, uint32_t H, uint32_t gridtype, int align_corners,
+                                  uint32_t interp, int dtype, float in_bound, int accumulate_f32,
+                                  const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream) {
+    (void)embeddings;
+    if (!grad || !inputs || !offsets || !grad_embeddings || !row_idx || !n_rows) return LNB_ERR_INVALID_ARGUMENT;
+    if (gridtype > 1 || interp > 1 || L == 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (B == 0) return LNB_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool ac = align_corners != 0;
+    const float2 norm = make_norm(in_bound);
+    const bool acc32 = accumulate_f32 != 0;
+    const void *dy_dx = nullptr;
+    void *grad_inputs = nullptr;
+    const int layout = LNB_LAYOUT_BLC;
+    LNB_GRID_DISPATCH(run_bwd, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs,
+                      gridtype, ac, interp, layout, norm, acc32, n_rows, st, row_idx);
 }
 
 int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *embeddings,

@@ -28,6 +28,10 @@ struct BwdArgs {
     Shape sh;
     float *wgrad;               // fp32, flat weight layout, accumulated with atomics
     const int32_t *n_active;
+    // Row compaction (nullable).  With row_idx, tile row r of the kernel is row row_idx[r] of every per-row INPUT
+    // (saved activations, X, sig_out, g_rgb, ...), *n_active is the EXACT number of valid rows (rows beyond it inside
+    // the last tile contribute nothing), and the per-row OUTPUTS (dX / g_sig_out) and the generic G are in compact order.
+    const int32_t *row_idx;
     // ---- generic mode ----
     const __half *G, *X;        // [B,16] gradient of the output, [B,in_dim] inputs
     __half *bbuf, *dX;          // nullable: [n_act,B,64] pre-activation gradients / [B,in_dim] input gradient
@@ -191,7 +195,13 @@ k_mlp_bwd(const BwdArgs a) {
     const uint32_t d_whid = d_wout + 32;
     const uint32_t d_win = d_whid + 64 * sh.n_hid;
 
-    const uint32_t n_tiles = active_rows(B, a.n_active) / kRows;
+    const int32_t *__restrict__ ridx = a.row_idx;
+    uint32_t n_valid = B;                                                  // rows that exist (compact mode: exact count)
+    if (ridx) {
+        const int32_t nv = *a.n_active;
+        n_valid = min(B, (uint32_t)(nv > 0 ? nv : 0));
+    }
+    const uint32_t n_tiles = ridx ? (n_valid + kRows - 1) / kRows : active_rows(B, a.n_active) / kRows;
     const uint32_t stride_tiles = gridDim.x * kTG;
     const uint32_t n_iter = (n_tiles + stride_tiles - 1) / stride_tiles;
     const bool want_dx = kHead || a.dX != nullptr;
@@ -261,17 +271,35 @@ k_mlp_bwd(const BwdArgs a) {
         const uint32_t n_enc_chunks = kHead ? (a.nfreq + 7) / 8 : 0;
         uint32_t par_done = 0;
 
+        // source row of tile row `rc` (compact numbering): identity without a row list; rows past the valid count
+        // read row 0 (any valid address) and are neutralised where they could contribute
+        auto src_row = [&](uint32_t rc) -> uint32_t { return ridx ? (rc < n_valid ? (uint32_t)__ldg(ridx + rc) : 0u) : rc; };
         auto load_head_row = [&](HeadRow &h, uint32_t tile) {
-            const size_t r = (size_t)tile * kRows + row;
+            const uint32_t rc = tile * kRows + row;
+            const size_t r = src_row(rc);
             h.rid = (uint32_t)__ldg(a.ray_ids + r);
             h.so_lo = __ldg(reinterpret_cast<const uint4 *>(a.sig_out + r * kOut));
             h.so_hi = __ldg(reinterpret_cast<const uint4 *>(a.sig_out + r * kOut) + 1);
             h.gr = __ldg(reinterpret_cast<const float2 *>(a.g_rgb) + r);
             h.pr = __ldg(reinterpret_cast<const float2 *>(a.rgb) + r);
             h.gs = __ldg(a.g_sigma + r);
+            if (rc >= n_valid) h.gr = make_float2(0.f, 0.f), h.gs = 0.f;     // padding row of the last compact tile
         };
-        auto load_act = [&](uint32_t layer, uint32_t tile) {
-            tg_load_tile64(gtid, s_h + layer * kTileBytes, a.fbuf + ((size_t)layer * B + (size_t)tile * kRows) * kHid);
+        // the four tile rows this thread copies chunks of (tg_load_tile64's mapping: row (gtid >> 3) + 32 j)
+        auto tile_rows4 = [&](uint32_t tile, uint32_t (&r4)[4]) {
+#pragma unroll
+            for (uint32_t j = 0; j < 4; ++j) r4[j] = src_row(tile * kRows + (gtid >> 3) + 32 * j);
+        };
+        auto load_act = [&](uint32_t layer, uint32_t tile, const uint32_t (&r4)[4]) {
+            const __half *src = a.fbuf + (size_t)layer * B * kHid;
+            if (!ridx) {
+                tg_load_tile64(gtid, s_h + layer * kTileBytes, src + (size_t)tile * kRows * kHid);
+            } else {
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j)
+                    cp_async16(tile_chunk_addr(s_h + layer * kTileBytes, (gtid >> 3) + 32 * j, gtid & 7),
+                               src + (size_t)r4[j] * kHid + (gtid & 7) * 8);
+            }
         };
         // inputs that live in the X / G tiles: free once the last MMA of the previous tile has retired
         auto load_xg = [&](uint32_t tile, const HeadRow &h) {
@@ -284,18 +312,31 @@ k_mlp_bwd(const BwdArgs a) {
                 // G: 16 valid columns (chunks 0,1); chunks 2..7 re-zeroed every tile because dH reuses this tile
                 for (uint32_t q = gtid; q < kRows * 8; q += kTGThreads) {
                     const uint32_t r = q >> 3, c = q & 7;
-                    cp_async16(tile_chunk_addr(s_g, r, c), a.G + (row0 + r) * kOut + (c < 2 ? c * 8 : 0), c < 2 ? 16u : 0u);
+                    const bool live = c < 2 && (!ridx || row0 + r < n_valid);      // padding rows of a compact tile: zeros
+                    cp_async16(tile_chunk_addr(s_g, r, c), a.G + (row0 + r) * kOut + (c < 2 ? c * 8 : 0), live ? 16u : 0u);
                 }
-                tg_load_tiles(gtid, s_x, a.X + row0 * sh.in_dim, sh.in_dim, sh.in_dim);
+                if (!ridx) {
+                    tg_load_tiles(gtid, s_x, a.X + row0 * sh.in_dim, sh.in_dim, sh.in_dim);
+                } else {
+                    const uint32_t cpr = sh.kt_in * 8;
+                    for (uint32_t q = gtid; q < kRows * cpr; q += kTGThreads) {
+                        const uint32_t r = q / cpr, c = q - r * cpr;
+                        if (c * 8 < sh.in_dim)
+                            cp_async16(tile_chunk_addr(s_x + (c >> 3) * kTileBytes, r, c & 7),
+                                       a.X + (size_t)src_row((uint32_t)row0 + r) * sh.in_dim + c * 8);
+                    }
+                }
             }
         };
 
         uint32_t tile = blockIdx.x * kTG + tg;
         bool have = tile < n_tiles;
         HeadRow hr = {};
+        uint32_t rows_next[4] = {0, 0, 0, 0};     // source rows of the NEXT tile's activation copies (compact mode)
         if (have) {
             if (kHead) load_head_row(hr, tile);
-            for (uint32_t l = 0; l < n_act; ++l) load_act(l, tile);
+            tile_rows4(tile, rows_next);
+            for (uint32_t l = 0; l < n_act; ++l) load_act(l, tile, rows_next);
             load_xg(tile, hr);
         }
         while (have) {
@@ -337,6 +378,7 @@ k_mlp_bwd(const BwdArgs a) {
             const bool have_next = next < n_tiles;
             HeadRow hn = {};
             if (kHead && have_next) load_head_row(hn, next);
+            if (ridx && have_next) tile_rows4(next, rows_next);
 
             // ---- layers, last to first: epilogue = ReLU mask, fp16, operand for the next MMA ----
             for (int layer = (int)sh.n_hid; layer >= 0; --layer) {
@@ -374,7 +416,7 @@ k_mlp_bwd(const BwdArgs a) {
                 }
                 // The `done` we just consumed retires every EARLIER MMA of this group (in-order pipe), in particular
                 // the previous phase's weight-gradient MMAs that read saved-activation tile layer + 1: refill it now.
-                if (have_next && layer < (int)sh.n_hid) load_act((uint32_t)layer + 1, next);
+                if (have_next && layer < (int)sh.n_hid) load_act((uint32_t)layer + 1, next, rows_next);
             }
             if (kHead) {
                 // ---- geo gradient + density gradient -> g_sig_out row (network.py:173 trunc_exp backward) ----
@@ -432,7 +474,7 @@ k_mlp_bwd(const BwdArgs a) {
             // every MMA of this tile has retired (last `done` wait above): activation tile 0 and the X / G tiles can
             // take the next tile
             if (have_next) {
-                load_act(0, next);
+                load_act(0, next, rows_next);
                 load_xg(next, hn);
             }
             fence_before_sync();          // orders this tile's TMEM reads before the next tile's MMAs

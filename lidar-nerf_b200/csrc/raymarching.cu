@@ -660,7 +660,7 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
                        float a_r, float a_i, float loss_scale, float *__restrict__ weights_sum,
                        float *__restrict__ depth, float *__restrict__ image, float *__restrict__ t0_out,
                        float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
-                       float *__restrict__ loss_out) {
+                       float *__restrict__ loss_out, int32_t *__restrict__ live_idx, int32_t *__restrict__ n_live) {
     constexpr int NCH = 2;
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
@@ -751,6 +751,7 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
     float c_in[NCH] = {0.f, 0.f};
     float d_in = 0.f, T_in = 1.0f, t_in = 0.f;
     uint32_t done = count;     // first sample index that received no gradient (early stop)
+    uint32_t n_used = count;   // samples up to and including the one that crossed the threshold
     for (uint32_t base = 0; base < count; base += 32) {
         const uint32_t i = base + lane;
         const bool valid = i < count;
@@ -790,6 +791,7 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
         }
         if (stop) {
             done = base + 32;
+            n_used = base + (uint32_t)__ffs(stop);
             break;
         }
         T_in = __shfl_sync(kFullMask, T_after, 31);
@@ -802,6 +804,14 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
         const size_t s = (size_t)offset + i;
         reinterpret_cast<float2 *>(grad_rgbs)[s] = make_float2(0.f, 0.f);
         grad_sigmas[s] = 0.f;
+    }
+    if (live_idx) {
+        // rows that can carry a gradient (the ray's samples up to the early stop), appended to a compact list in
+        // arrival order: the backward kernels walk this list instead of all marched rows
+        uint32_t at = 0;
+        if (lane == 0) at = (uint32_t)atomicAdd(n_live, (int)n_used);
+        at = __shfl_sync(kFullMask, at, 0);
+        for (uint32_t i = lane; i < n_used; i += 32) live_idx[at + i] = (int32_t)(offset + i);
     }
 }
 
@@ -1046,7 +1056,9 @@ int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float
                               uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
                               uint32_t N, float T_thresh, float alpha_d, float alpha_r, float alpha_i,
                               float loss_scale, float *weights_sum, float *depth, float *image, float *t0,
-                              float *grad_sigmas, float *grad_rgbs, float *loss_out, lnb_stream_t stream) {
+                              float *grad_sigmas, float *grad_rgbs, float *loss_out, int32_t *live_idx,
+                              int32_t *n_live, lnb_stream_t stream) {
+    LNB_REQUIRE((live_idx == nullptr) == (n_live == nullptr));
     LNB_REQUIRE(rays && gt && nears && noises && weights_sum && depth && image && loss_out);
     LNB_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs));
     LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && max_steps >= 1);
@@ -1056,7 +1068,8 @@ int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float
     const float dt_max = two_sqrt3 * (1 << (C - 1)) / H;
     k_lidar_composite_step<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
         sigmas, rgbs, deltas, rays, gt, nears, noises, dt_gamma, dt_min, dt_max, counter, M, N, T_thresh, alpha_d,
-        alpha_r, alpha_i, loss_scale, weights_sum, depth, image, t0, grad_sigmas, grad_rgbs, loss_out);
+        alpha_r, alpha_i, loss_scale, weights_sum, depth, image, t0, grad_sigmas, grad_rgbs, loss_out, live_idx,
+        n_live);
     count_launch();
     return launch_status();
 }

@@ -61,6 +61,8 @@ class FieldConfig:
     perturb: bool = True                 # jitter the march start (Trainer.train_step passes perturb=True)
     fused_field: bool = True             # density MLP + LiDAR head as the fused field kernels (csrc/field.cu)
     fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
+    compact_backward: bool = True        # backward kernels walk only the samples up to each ray's early stop
+    late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam
     seed: int = 0
 
     @property
@@ -130,7 +132,7 @@ class LidarFieldEngine:
         self.density_grid = torch.zeros(c.cascade, H3, dtype=torch.float32, device=dev)
         self.prior_grid = torch.zeros(c.cascade, H3, dtype=torch.float32, device=dev)    # LiDAR free-space prior
         self.bitfield = torch.full((c.cascade * H3 // 8,), 255, dtype=torch.uint8, device=dev)
-        self.counter = torch.zeros(2, dtype=torch.int32, device=dev)
+        self.counter = torch.zeros(4, dtype=torch.int32, device=dev)      # (samples, rays, live samples, -)
         self.mean_density = 0.0
 
         # ---- static per-ray buffers ------------------------------------------------------------------------
@@ -180,6 +182,7 @@ class LidarFieldEngine:
         self.xyzs = torch.zeros(M, 3, **f)
         self.dirs = torch.zeros(M, 3, **f) if not self.fused else None
         self.ray_ids = torch.zeros(M, dtype=torch.int32, device=dev)
+        self.live_idx = torch.zeros(M, dtype=torch.int32, device=dev)      # rows that can carry a gradient, compact
         self.deltas = torch.zeros(M, 2, **f)
         self.enc = torch.empty(M, self.enc_dim, **h)
         self.sig_out = torch.empty(M, 16, **h)
@@ -233,6 +236,8 @@ class LidarFieldEngine:
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
         # (the extended march also zeroes the padding rows of the last tile)
         na = p(self.counter)
+        compact = bool(c.compact_backward and c.fused_composite and self.fused)
+        nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
@@ -261,7 +266,8 @@ class LidarFieldEngine:
                                              u32(c.cascade), u32(c.grid_size), na, u32(M), u32(N), f32(c.T_thresh),
                                              f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale),
                                              p(self.ws), p(self.depth), p(self.image), p(self.t0), p(self.g_sigma),
-                                             p(self.g_rgb), p(self.loss_acc), s), "lidar_composite_step")
+                                             p(self.g_rgb), p(self.loss_acc), p(self.live_idx) if compact else vp(0),
+                                             nl if compact else vp(0), s), "lidar_composite_step")
         else:
             rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2,
                                                self.ws, self.depth, self.image)
@@ -274,6 +280,32 @@ class LidarFieldEngine:
             rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb,
                                                 self.deltas, self.rays, self.ws, self.depth, self.image, M, N,
                                                 c.T_thresh, 2, self.g_sigma, self.g_rgb)
+        if c.late_grad_zero:
+            # The 55 MB fp32 gradient table is cleared HERE, a few microseconds before the scatter-add, instead of by
+            # Adam half a millisecond (and ~1 GB of other traffic) earlier: the zeroed lines are still in the 126 MB L2
+            # when the atomics arrive, so they do not have to be fetched back from HBM one 32-byte sector at a time.
+            self.G[self.n_table:].zero_()
+        if compact:
+            # backward on the live rows only: g_sig_out / g_enc are in compact order, everything saved by the forward
+            # pass is read through live_idx
+            li = p(self.live_idx)
+            _ck(lib.lnb_field_head_backward_rows(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
+                                                 p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
+                                                 u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+                                                 u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
+                                                 p(self.g_head_w), li, nl, s), "field_head_backward_rows")
+            _ck(lib.lnb_ffmlp_backward_accumulate_rows(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h),
+                                                       p(self.fb_sigma), u32(M), u32(self.enc_dim), u32(16),
+                                                       u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), i32(1),
+                                                       p(self.g_enc), p(self.g_sigma_w), li, nl, s),
+                "ffmlp_bwd_rows(sigma)")
+            if c.late_grad_zero:
+                self.g_table.zero_()
+            _ck(lib.lnb_grid_encode_backward_rows(p(self.g_enc), p(self.xyzs), p(self.table_h), p(self.offsets),
+                                                  p(self.g_table), u32(M), u32(3), u32(c.level_dim), u32(c.num_levels),
+                                                  f32(self.S), u32(c.base_resolution), u32(0), i32(0), u32(0), i32(1),
+                                                  f32(c.bound), i32(1), li, nl, s), "grid_bwd_rows")
+            return
         if self.fused:
             _ck(lib.lnb_field_head_backward(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                             p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
@@ -294,6 +326,8 @@ class LidarFieldEngine:
                                               u32(M), u32(self.enc_dim), u32(16), u32(c.hidden_dim),
                                               u32(c.sigma_layers), u32(0), u32(6), i32(1), p(self.g_enc),
                                               p(self.g_sigma_w), na, s), "ffmlp_bwd(sigma)")
+        if c.late_grad_zero:
+            self.g_table.zero_()
         _ck(lib.lnb_grid_encode_backward_ex(p(self.g_enc), p(self.xyzs), p(self.table_h), p(self.offsets),
                                             p(self.g_table), u32(M), u32(3), u32(c.level_dim), u32(c.num_levels),
                                             f32(self.S), u32(c.base_resolution), vp(0), vp(0), u32(0), i32(0), u32(0),
@@ -307,10 +341,11 @@ class LidarFieldEngine:
         lr = c.lr if lr is None else lr
         if self.ex.world == 1:
             adam_step(self.P, self.G, self.m, self.v, self.Ph, lr, c.beta1, c.beta2, c.eps, self.step_count,
-                      grad_scale=1.0 / c.loss_scale, zero_grad=True)
+                      grad_scale=1.0 / c.loss_scale, zero_grad=not c.late_grad_zero)
             return
         self.ex.reduce_scatter(self.G, self.G_shard)
-        self.G.zero_()
+        if not c.late_grad_zero:
+            self.G.zero_()
         adam_step(self.P, self.G_shard, self.m, self.v, self.Ph_shard, lr, c.beta1, c.beta2, c.eps, self.step_count,
                   grad_scale=dp.grad_scale(c.loss_scale), zero_grad=False)
         self.ex.all_gather(self.Ph, self.Ph_shard)

@@ -71,6 +71,30 @@ def test_fused_composite_step_equals_the_three_kernel_chain():
     np.testing.assert_allclose(a["gpu"]["loss"], b["gpu"]["loss"], rtol=1e-5)
 
 
+def test_compact_backward_equals_backward_over_all_rows():
+    """The backward kernels on the live-row list (samples up to each ray's early stop) give the gradient of the
+    backward pass over every marched row: the skipped rows carry exactly zero."""
+    from oracle import check_engine
+    out = {}
+    for compact in (False, True):
+        cfg = check_engine.small_config(perturb=False, compact_backward=compact, T_thresh=1e-2, density_scale=50.0)
+        eng, gpu, cpu = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg)
+        out[compact] = (eng, gpu)
+        check_engine.compare(gpu, cpu, eng.n_table)
+    (e0, g0), (e1, g1) = out[False], out[True]
+    a, b = g1["grad"].astype(np.float64), g0["grad"].astype(np.float64)
+    assert np.linalg.norm(a - b) / np.linalg.norm(b) < 1e-3
+    # the live list: every ray's samples up to the first one that received a zero gradient because of the early stop
+    n, n_live = int(e1.counter[0].item()), int(e1.counter[2].item())
+    assert 0 < n_live < 0.9 * n, (n, n_live)
+    live = np.sort(e1.live_idx[:n_live].cpu().numpy())
+    assert len(np.unique(live)) == n_live and live.max() < n
+    dead = np.setdiff1d(np.arange(n), live)
+    assert (e1.g_sigma.cpu().numpy()[dead] == 0).all() and (e1.g_rgb.cpu().numpy()[dead] == 0).all()
+    nz = np.nonzero((e1.g_sigma.cpu().numpy()[:n] != 0) | (e1.g_rgb.cpu().numpy()[:n] != 0).any(-1))[0]
+    assert np.isin(nz, live).all(), "a row with a gradient is missing from the live list"
+
+
 def test_fused_step_full_size_table_matches_cpu_restatement():
     from oracle import check_engine
     cfg = check_engine.small_config(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
