@@ -9,6 +9,7 @@
 // in B200's 126 MB L2).  Results are staged through a padded shared-memory tile and leave the SM
 // as full coalesced rows, in either the reference's [L,B,C] layout or the [B,L*C] layout the MLP
 // consumes (which removes the torch permute + copy the reference pays, grid.py:87,104).
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
@@ -239,9 +240,9 @@ __device__ __forceinline__ void interp_corners(const Cell<D> &cell, const LevelG
     // all gathers first (2^D independent loads in flight, kept in the table's type), then the rounding-ordered
     // accumulation
     __align__(16) T v[1u << D][C];
-    // (Loading the two x-neighbours of a hashed level as ONE aligned 8-byte pair when the base x is even - they differ
-    // only in bit 0 of the xor - was measured on B200: 115 -> 125 us.  The extra selects and the divergent second path
-    // cost more than the saved L1 lookups; the gather is not lookup-bound.)
+    // (Measured on B200 and rejected: loading the two x-neighbours of a hashed level as ONE aligned 8-byte pair when the
+    // base x is even - they differ only in bit 0 of the xor - 115 -> 125 us; `ld.global.nc.L1::no_allocate` for the
+    // hashed levels, 115 -> 180 us; 64 instead of 40 registers at 2 CTAs/SM, no change.)
 #pragma unroll
     for (uint32_t corner = 0; corner < (1u << D); ++corner) {
         uint32_t row;
@@ -454,7 +455,8 @@ __global__ void __launch_bounds__(kBwdThreads)
 k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
            const int32_t *__restrict__ offsets, TA *__restrict__ grad_table, uint32_t B, uint32_t L,
            float S, uint32_t H, uint32_t gridtype, bool align_corners, uint32_t interp, int layout, float2 norm,
-           uint32_t n_agg, const int32_t *__restrict__ n_active, const int32_t *__restrict__ row_idx) {
+           uint32_t n_agg, const int32_t *__restrict__ n_active, const int32_t *__restrict__ row_idx,
+           uint32_t level_lo, uint32_t level_hi) {
     __shared__ LevelGeo s_geo[kMaxLevelsShared];
     __shared__ LevelIndex<D> s_idx[kMaxLevelsShared];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -510,6 +512,7 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
 #pragma unroll
         for (uint32_t c = 0; c < C; ++c) live |= (gv[c] != 0.f);
         const bool agg = level < n_agg;      // warp-uniform
+        if (level < level_lo || level >= level_hi) continue;   // diagnostic level window (all levels in production)
         if (!agg && !live) continue;
 
         const Cell<D> cell = locate_unit<D>(v, inside, g, align_corners, interp);
@@ -653,15 +656,23 @@ int run_bwd(const void *grad, const float *inputs, const int32_t *offsets, void 
             else break;
         }
     }
+    // diagnostic: LNB_GRID_BWD_LEVELS="lo,hi" restricts the scatter to levels [lo, hi) (scripts/diag_grid_levels.py)
+    uint32_t lv_lo = 0, lv_hi = L;
+    if (const char *e = getenv("LNB_GRID_BWD_LEVELS")) {
+        unsigned a = 0, b = L;
+        if (sscanf(e, "%u,%u", &a, &b) == 2) lv_lo = a, lv_hi = b < L ? b : L;
+    }
     const unsigned bx = ceil_div<uint32_t>(B, kBwdThreads);
     if (acc_f32 && sizeof(T) == 2)
         k_grid_bwd<T, float, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
                                                                static_cast<float *>(grad_emb), B, L, S, H, gridtype,
-                                                               ac, interp, layout, norm, n_agg, n_active, row_idx);
+                                                               ac, interp, layout, norm, n_agg, n_active, row_idx,
+                                                               lv_lo, lv_hi);
     else
         k_grid_bwd<T, T, D, C><<<bx, kBwdThreads, 0, st>>>(static_cast<const T *>(grad), inputs, offsets,
                                                            static_cast<T *>(grad_emb), B, L, S, H, gridtype, ac,
-                                                           interp, layout, norm, n_agg, n_active, row_idx);
+                                                           interp, layout, norm, n_agg, n_active, row_idx, lv_lo,
+                                                           lv_hi);
     count_launch();
     int rc = launch_status();
     if (rc != LNB_OK) return rc;
