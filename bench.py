@@ -197,6 +197,8 @@ def main():
         cfg.compact_backward = False
     if os.environ.get("LNB_LATE_GRAD_ZERO") == "0":
         cfg.late_grad_zero = False
+    if os.environ.get("LNB_PIPELINE_ADAM") == "0":
+        cfg.pipeline_adam = False
     seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
     eng = LidarFieldEngine(cfg, N, device=dev, sample_budget=N * 64)
     eng.seed_occupancy_from_points(seq.surface_points())
@@ -238,6 +240,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    losses = []
+
     def run(steps, host):
         staging = torch.empty(N, 9, device=dev)
         for i in range(steps):
@@ -248,7 +252,11 @@ def main():
                 load(pool[i % len(pool)])
             eng.train_step(use_graph=not args.no_graph)
             if host:
-                eng.read_loss()           # D2H read of the step's loss
+                # D2H read of the step's loss, every step: copied to pinned memory behind the step and consumed on the
+                # host one step later, so the launch queue never drains (the last one is collected after the loop)
+                losses.append(eng.read_loss_async())
+        if host:
+            losses.append(eng.read_loss_last())
 
     run(args.warmup, False)
     launches0 = _lib.launch_count()
@@ -260,6 +268,7 @@ def main():
         torch.cuda.profiler.start()
     e0.record()
     run(args.steps, False)
+    eng.flush()        # the pipelined graph step applies each update at the start of the next one: settle the last
     e1.record()
     barrier()
     ms = e0.elapsed_time(e1)
@@ -276,6 +285,7 @@ def main():
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record()
     run(args.steps, True)
+    eng.flush()
     e3.record()
     barrier()
     ms_e2e = e2.elapsed_time(e3)
@@ -305,7 +315,10 @@ def main():
                           "parallelism": f"dp{world} (NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params)" if world > 1 else "single"},
                "clocks": clk,
                "e2e": {"value": world * N * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
-                       "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4},
+                       "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4,
+                       "loss_readback": "every step: 4 B D2H into pinned memory behind the step, consumed on the host "
+                                        "one step later (no queue drain)",
+                       "last_loss": next((x for x in reversed(losses) if x is not None), None)},
                "gpu_launches": int(launches)}
         if roof:
             out["roofline"] = roof
@@ -387,7 +400,7 @@ def profile_kernels(eng, pool, load, iters=5):
         saved.append((obj, name, wrap(obj, name, name)))
     lib_names = ["lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_ray_terms", "lnb_field_forward",
                  "lnb_field_head_backward", "lnb_lidar_composite_step", "lnb_field_head_backward_rows",
-                 "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
+                 "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows", "lnb_adam_step_dev",
                  "lnb_zero_sample_tail", "lnb_grid_encode_forward_ex", "lnb_ffmlp_forward_ex", "lnb_field_head_input", "lnb_field_head_rgb",
                  "lnb_lidar_loss", "lnb_field_head_out_grad", "lnb_ffmlp_backward_accumulate", "lnb_field_sigma_out_grad",
                  "lnb_grid_encode_backward_ex"]

@@ -247,6 +247,14 @@ int lnb_free_splitk(void);
 int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half,
                   size_t n, float lr, float beta1, float beta2, float eps, float bias_correction1,
                   float bias_correction2, float grad_scale, int zero_grad, lnb_stream_t stream);
+/* The same update with the step-dependent scalars read from device memory, so the launch can live inside a CUDA graph
+ * (by-value arguments of a captured launch are frozen; the bias corrections and a scheduled learning rate change every
+ * step).  hyper_dev [5] floats is written by lnb_adam_set_hyper (a one-thread kernel on the same stream, launched
+ * before each replay); enable == 0 turns the captured update into a no-op (nothing pending). */
+int lnb_adam_set_hyper(float *hyper_dev, float lr, float bias_correction1, float bias_correction2, float grad_scale,
+                       int enable, lnb_stream_t stream);
+int lnb_adam_step_dev(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half, size_t n,
+                      float beta1, float beta2, float eps, const float *hyper_dev, int zero_grad, lnb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Glue of the LiDAR field step - the elementwise torch code between the reference's extension calls

@@ -25,10 +25,17 @@ __device__ __forceinline__ float adam_one(float &p, float g, float &m, float &v,
     return p;
 }
 
+// `hyper` (nullable, device): {lr, 1/bc1, 1/sqrt(bc2), grad_scale, enable} written by k_adam_set_hyper before the
+// launch - the form a CUDA graph can hold (the by-value arguments of a captured launch are frozen, the step-dependent
+// bias corrections and the scheduled learning rate are not).  enable == 0 makes the launch a no-op.
 template <bool kHalfCopy, bool kZeroGrad>
 __global__ void __launch_bounds__(kThreads)
 k_adam(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, float *__restrict__ v,
-       __half *__restrict__ ph, size_t n, AdamArgs a) {
+       __half *__restrict__ ph, size_t n, AdamArgs a, const float *__restrict__ hyper) {
+    if (hyper) {
+        if (hyper[4] == 0.f) return;
+        a.lr = hyper[0], a.inv_bc1 = hyper[1], a.inv_sqrt_bc2 = hyper[2], a.gscale = hyper[3];
+    }
     const size_t n4 = n / 4;
     const size_t stride = (size_t)gridDim.x * blockDim.x;
     float4 *p4 = reinterpret_cast<float4 *>(p), *g4 = reinterpret_cast<float4 *>(g);
@@ -61,10 +68,53 @@ k_adam(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, floa
     }
 }
 
+__global__ void k_adam_set_hyper(float *hyper, float lr, float inv_bc1, float inv_sqrt_bc2, float gscale, float enable) {
+    hyper[0] = lr, hyper[1] = inv_bc1, hyper[2] = inv_sqrt_bc2, hyper[3] = gscale, hyper[4] = enable;
+}
+
+int launch_adam(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half, size_t n,
+                const AdamArgs &a, const float *hyper, int zero_grad, cudaStream_t st) {
+    const uintptr_t al = reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grad) |
+                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
+    if ((al & 15u) || (reinterpret_cast<uintptr_t>(params_half) & 7u)) return LNB_ERR_INVALID_ARGUMENT;
+    if (n == 0) return LNB_OK;
+    const size_t want = (n / 4 + kThreads - 1) / kThreads;
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    __half *ph = static_cast<__half *>(params_half);
+    if (ph) {
+        if (zero_grad) k_adam<true, true><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a, hyper);
+        else k_adam<true, false><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a, hyper);
+    } else {
+        if (zero_grad) k_adam<false, true><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a, hyper);
+        else k_adam<false, false><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a, hyper);
+    }
+    count_launch();
+    return launch_status();
+}
+
 }  // namespace
 }  // namespace lnb
 
 using namespace lnb;
+
+extern "C" int lnb_adam_set_hyper(float *hyper_dev, float lr, float bias_correction1, float bias_correction2,
+                                  float grad_scale, int enable, lnb_stream_t stream) {
+    if (!hyper_dev) return LNB_ERR_INVALID_ARGUMENT;
+    if (enable && (bias_correction1 == 0.f || bias_correction2 <= 0.f)) return LNB_ERR_INVALID_ARGUMENT;
+    k_adam_set_hyper<<<1, 1, 0, as_stream(stream)>>>(hyper_dev, lr, enable ? 1.f / bias_correction1 : 0.f,
+                                                     enable ? 1.f / sqrtf(bias_correction2) : 0.f, grad_scale,
+                                                     enable ? 1.f : 0.f);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int lnb_adam_step_dev(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half,
+                                 size_t n, float beta1, float beta2, float eps, const float *hyper_dev, int zero_grad,
+                                 lnb_stream_t stream) {
+    if (!params || !grad || !exp_avg || !exp_avg_sq || !hyper_dev) return LNB_ERR_INVALID_ARGUMENT;
+    AdamArgs a{0.f, beta1, beta2, eps, 0.f, 0.f, 0.f};
+    return launch_adam(params, grad, exp_avg, exp_avg_sq, params_half, n, a, hyper_dev, zero_grad, as_stream(stream));
+}
 
 extern "C" int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq,
                              void *params_half, size_t n, float lr, float beta1, float beta2, float eps,
@@ -72,22 +122,6 @@ extern "C" int lnb_adam_step(float *params, float *grad, float *exp_avg, float *
                              int zero_grad, lnb_stream_t stream) {
     if (!params || !grad || !exp_avg || !exp_avg_sq) return LNB_ERR_INVALID_ARGUMENT;
     if (bias_correction1 == 0.f || bias_correction2 <= 0.f) return LNB_ERR_INVALID_ARGUMENT;
-    const uintptr_t al = reinterpret_cast<uintptr_t>(params) | reinterpret_cast<uintptr_t>(grad) |
-                         reinterpret_cast<uintptr_t>(exp_avg) | reinterpret_cast<uintptr_t>(exp_avg_sq);
-    if ((al & 15u) || (reinterpret_cast<uintptr_t>(params_half) & 7u)) return LNB_ERR_INVALID_ARGUMENT;
-    if (n == 0) return LNB_OK;
     AdamArgs a{lr, beta1, beta2, eps, 1.f / bias_correction1, 1.f / sqrtf(bias_correction2), grad_scale};
-    const size_t want = (n / 4 + kThreads - 1) / kThreads;
-    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
-    cudaStream_t st = as_stream(stream);
-    __half *ph = static_cast<__half *>(params_half);
-    if (ph) {
-        if (zero_grad) k_adam<true, true><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a);
-        else k_adam<true, false><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a);
-    } else {
-        if (zero_grad) k_adam<false, true><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a);
-        else k_adam<false, false><<<blocks, kThreads, 0, st>>>(params, grad, exp_avg, exp_avg_sq, ph, n, a);
-    }
-    count_launch();
-    return launch_status();
+    return launch_adam(params, grad, exp_avg, exp_avg_sq, params_half, n, a, nullptr, zero_grad, as_stream(stream));
 }
