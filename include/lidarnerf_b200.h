@@ -150,6 +150,12 @@ int lnb_grid_encode_backward(const void *grad, const float *inputs, const void *
                              uint32_t C, uint32_t L, float S, uint32_t H, const void *dy_dx,
                              void *grad_inputs, uint32_t gridtype, int align_corners,
                              uint32_t interp, int dtype, int layout, lnb_stream_t stream);
+/* _gridencoder.grad_total_variation (gridencoder/src/bindings.cpp:10, gridencoder.cu:695-911): adds the gradient of a
+ * total-variation penalty over the cells that contain `inputs` [B,D] (in [0,1], SAME dtype as the table - the
+ * reference reinterprets the inputs as scalar_t) to `grad` (table layout, table dtype).  No caller in the reference. */
+int lnb_grad_total_variation(const void *inputs, const void *embeddings, void *grad, const int32_t *offsets,
+                             float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             uint32_t gridtype, int align_corners, int dtype, lnb_stream_t stream);
 
 /* Extensions used by the fused training step:
  *  - `in_bound` > 0: inputs are world coordinates in [-bound, bound], mapped to [0,1] inside the kernel exactly
@@ -363,6 +369,34 @@ int lnb_grid_encode_backward_rows(const void *grad, const float *inputs, const v
                                   uint32_t interp, int dtype, float in_bound, int accumulate_f32,
                                   const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * Evaluation-side callers of the hot path: range image <-> point cloud
+ * (lidarnerf/convert.py) and the Chamfer nearest-neighbour search (extern/chamfer3D/chamfer3D.cu).
+ * ---------------------------------------------------------------------------------------- */
+
+/* chamfer_3D.forward (extern/chamfer3D/chamfer_cuda.cpp:26-33, chamfer3D.cu:135-166): xyz1 [B,N,3], xyz2 [B,M,3] ->
+ * dist1 [B,N] / idx1 [B,N] = squared distance to / index of the nearest xyz2 point (first minimum), and the same
+ * for xyz2 against xyz1. */
+int lnb_chamfer_forward(const float *xyz1, const float *xyz2, uint32_t B, uint32_t N, uint32_t M, float *dist1,
+                        float *dist2, int32_t *idx1, int32_t *idx2, lnb_stream_t stream);
+/* chamfer_3D.backward (chamfer_cuda.cpp:35-45, chamfer3D.cu:167-236): ADDS into grad_xyz1 / grad_xyz2 (caller zeroes) */
+int lnb_chamfer_backward(const float *xyz1, const float *xyz2, float *grad_xyz1, float *grad_xyz2,
+                         const float *grad_dist1, const float *grad_dist2, const int32_t *idx1, const int32_t *idx2,
+                         uint32_t B, uint32_t N, uint32_t M, lnb_stream_t stream);
+/* lidar_to_pano_with_intensities (lidarnerf/convert.py:99-160): points [N, point_stride >= 3] (x, y, z[, intensity])
+ * in the sensor frame -> pano [H,W] (range of the closest point of each pixel, 0 = empty) and intensities [H,W]
+ * (nullable; 0 when point_stride == 3).  workspace: lnb_lidar_to_pano_workspace_bytes(H, W) bytes. */
+size_t lnb_lidar_to_pano_workspace_bytes(uint32_t H, uint32_t W);
+int lnb_lidar_to_pano(const float *points, uint32_t point_stride, uint32_t N, uint32_t H, uint32_t W, float fov_up,
+                      float fov, float max_depth, float *pano, float *intensities, void *workspace,
+                      lnb_stream_t stream);
+/* pano_to_lidar_with_intensities (lidarnerf/convert.py:194-235): every non-empty pixel -> (x, y, z, intensity) along
+ * its beam, in row-major pixel order; points_out [H*W,4] (16-byte aligned), count_out[0] = number of points.
+ * workspace: lnb_pano_to_lidar_workspace_bytes(H, W) bytes. */
+size_t lnb_pano_to_lidar_workspace_bytes(uint32_t H, uint32_t W);
+int lnb_pano_to_lidar(const float *pano, const float *intensities, uint32_t H, uint32_t W, float fov_up, float fov,
+                      float *points_out, int32_t *count_out, void *workspace, lnb_stream_t stream);
 
 #ifdef __cplusplus
 }

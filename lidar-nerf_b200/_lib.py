@@ -22,6 +22,9 @@ lib.lnb_arch.restype = C.c_char_p
 lib.lnb_launch_count.restype = C.c_uint64
 lib.lnb_ffmlp_backward_workspace_bytes.restype = C.c_size_t
 lib.lnb_ffmlp_backward_workspace_bytes.argtypes = [C.c_uint32] * 4
+for _n in ("lnb_lidar_to_pano_workspace_bytes", "lnb_pano_to_lidar_workspace_bytes"):
+    getattr(lib, _n).restype = C.c_size_t
+    getattr(lib, _n).argtypes = [C.c_uint32] * 2
 
 u32, f32, i32, vp, sz = C.c_uint32, C.c_float, C.c_int, C.c_void_p, C.c_size_t
 
@@ -32,7 +35,7 @@ SYMBOLS = [
     "lnb_march_rays_train", "lnb_composite_rays_train_forward", "lnb_composite_rays_train_backward",
     "lnb_composite_rays_train_forward_ex", "lnb_composite_rays_train_backward_ex",
     "lnb_march_rays", "lnb_composite_rays",
-    "lnb_grid_encode_forward", "lnb_grid_encode_backward",
+    "lnb_grid_encode_forward", "lnb_grid_encode_backward", "lnb_grad_total_variation",
     "lnb_freq_encode_forward", "lnb_freq_encode_backward",
     "lnb_sh_encode_forward", "lnb_sh_encode_backward",
     "lnb_ffmlp_forward", "lnb_ffmlp_inference", "lnb_ffmlp_backward_workspace_bytes", "lnb_ffmlp_backward",
@@ -42,6 +45,8 @@ SYMBOLS = [
     "lnb_field_forward", "lnb_field_head_backward",
     "lnb_zero_sample_tail", "lnb_field_head_input", "lnb_field_head_rgb", "lnb_lidar_loss",
     "lnb_field_head_out_grad", "lnb_field_sigma_out_grad", "lnb_lidar_rays", "lnb_lidar_composite_step",
+    "lnb_chamfer_forward", "lnb_chamfer_backward", "lnb_lidar_to_pano_workspace_bytes", "lnb_lidar_to_pano",
+    "lnb_pano_to_lidar_workspace_bytes", "lnb_pano_to_lidar",
     "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
 ]
 

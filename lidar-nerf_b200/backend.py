@@ -173,9 +173,15 @@ class _GridEncoder:
                                            i32(layout), _stream()), "grid_encode_backward")
 
     @staticmethod
-    def grad_total_variation(*args, **kwargs):
-        # gridencoder.cu:695-911 has no caller in the reference - out of scope.
-        raise NotImplementedError("grad_total_variation is outside the hot path this library implements")
+    def grad_total_variation(inputs, embeddings, grad, offsets, weight, B, D, C, L, S, H, gridtype, align_corners):
+        """gridencoder/src/bindings.cpp:10.  `inputs` must have the table's dtype (the reference reads them as scalar_t)."""
+        dt = _grid_dtype(embeddings, "embeddings")
+        if inputs.dtype != embeddings.dtype or grad.dtype != embeddings.dtype:
+            raise RuntimeError("grad_total_variation: inputs, embeddings and grad must share one dtype")
+        check(lib.lnb_grad_total_variation(_ptr(inputs, "inputs", embeddings.dtype), _ptr(embeddings, "embeddings"),
+                                           _ptr(grad, "grad", embeddings.dtype), _ip(offsets, "offsets"), f32(weight),
+                                           u32(B), u32(D), u32(C), u32(L), f32(S), u32(H), u32(gridtype),
+                                           i32(int(bool(align_corners))), i32(dt), _stream()), "grad_total_variation")
 
 
 # ------------------------------------------------------------------------------------------ _freqencoder

@@ -608,6 +608,68 @@ k_grid_input_bwd(const T *__restrict__ grad, const T *__restrict__ dy_dx, T *__r
     grad_inputs[t] = acc;
 }
 
+// gridencoder.cu:695-808 of the reference: total-variation regulariser added to the table gradient.  For the cell that
+// contains each input, on every level: grad[cell] += w * sum_nb (cell - nb) / sqrt(sum_nb (cell - nb)^2 + 1e-9), the
+// neighbours being the <= 2 D axis neighbours inside [0, resolution]; w = weight / (2 D) in the table's type.
+template <typename T, uint32_t D, uint32_t C>
+__global__ void __launch_bounds__(256)
+k_grid_tv(const T *__restrict__ inputs, const T *__restrict__ table, T *__restrict__ grad,
+          const int32_t *__restrict__ offsets, float weight, uint32_t B, uint32_t L, float S, uint32_t H,
+          uint32_t gridtype, bool align_corners) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const uint32_t level = blockIdx.y;
+    const LevelGeo g = level_geo(offsets, level, S, H);
+    const T *tab = table + (size_t)g.table_offset * C;
+    T *gt = grad + (size_t)g.table_offset * C;
+    uint32_t pg[D];
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        const float x = Num<T>::to_f(inputs[(size_t)b * D + d]);
+        if (x < 0 || x > 1) return;
+        pg[d] = (uint32_t)floorf(x * g.scale + (align_corners ? 0.0f : 0.5f));
+    }
+    T res[C], idelta[C];
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) res[c] = Num<T>::from_f(0.f), idelta[c] = Num<T>::from_f(0.f);
+    const uint32_t index = cell_row<D>(pg, gridtype, align_corners, g) * C;
+    const T w = Num<T>::from_f(weight / (2 * D));
+#pragma unroll
+    for (uint32_t d = 0; d < D; ++d) {
+        const uint32_t cur = pg[d];
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            if (side == 0 ? !(cur < g.resolution) : !(cur > 0)) continue;
+            pg[d] = side == 0 ? cur + 1 : cur - 1;
+            const uint32_t nb = cell_row<D>(pg, gridtype, align_corners, g) * C;
+#pragma unroll
+            for (uint32_t c = 0; c < C; ++c) {
+                // every operation rounds to T, as the reference's scalar_t arithmetic does
+                const T gv = Num<T>::from_f(Num<T>::to_f(tab[index + c]) - Num<T>::to_f(tab[nb + c]));
+                res[c] = Num<T>::from_f(Num<T>::to_f(res[c]) + Num<T>::to_f(gv));
+                idelta[c] = Num<T>::from_f(Num<T>::to_f(idelta[c]) +
+                                           Num<T>::to_f(Num<T>::from_f(Num<T>::to_f(gv) * Num<T>::to_f(gv))));
+            }
+        }
+        pg[d] = cur;
+    }
+#pragma unroll
+    for (uint32_t c = 0; c < C; ++c) {
+        const T wr = Num<T>::from_f(Num<T>::to_f(w) * Num<T>::to_f(res[c]));
+        atomic_add_one(gt + index + c, Num<T>::to_f(wr) * rsqrtf(Num<T>::to_f(idelta[c]) + 1e-9f));
+    }
+}
+
+template <typename T, uint32_t D, uint32_t C>
+int run_tv(const void *inputs, const void *emb, void *grad, const int32_t *offsets, float weight, uint32_t B, uint32_t L,
+           float S, uint32_t H, uint32_t gridtype, bool ac, cudaStream_t st) {
+    const dim3 grid(ceil_div<uint32_t>(B, 256), L, 1);
+    k_grid_tv<T, D, C><<<grid, 256, 0, st>>>(static_cast<const T *>(inputs), static_cast<const T *>(emb),
+                                             static_cast<T *>(grad), offsets, weight, B, L, S, H, gridtype, ac);
+    count_launch();
+    return launch_status();
+}
+
 inline uint32_t agg_max_resolution() {
     static int v = -1;
     if (v < 0) {
@@ -778,6 +840,17 @@ int lnb_grid_encode_backward_ex(const void *grad, const float *inputs, const voi
     const bool acc32 = accumulate_f32 != 0;
     LNB_GRID_DISPATCH(run_bwd, grad, inputs, offsets, grad_embeddings, B, L, S, H, dy_dx, grad_inputs,
                       gridtype, ac, interp, layout, norm, acc32, n_active, st);
+}
+
+int lnb_grad_total_variation(const void *inputs, const void *embeddings, void *grad, const int32_t *offsets,
+                             float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                             uint32_t gridtype, int align_corners, int dtype, lnb_stream_t stream) {
+    if (!inputs || !embeddings || !grad || !offsets) return LNB_ERR_INVALID_ARGUMENT;
+    if (gridtype > 1 || L == 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (B == 0) return LNB_OK;
+    cudaStream_t st = as_stream(stream);
+    const bool ac = align_corners != 0;
+    LNB_GRID_DISPATCH(run_tv, inputs, embeddings, grad, offsets, weight, B, L, S, H, gridtype, ac, st);
 }
 
 int lnb_grid_encode_backward_rows(const void *grad, const float *inputs, const void *embeddings,

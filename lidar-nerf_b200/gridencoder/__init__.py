@@ -121,9 +121,22 @@ class GridEncoder(nn.Module):
                           flat.requires_grad, self.gridtype_id, self.align_corners, self.interp_id)
         return out.view(lead + [self.output_dim])
 
-    def grad_total_variation(self, *args, **kwargs):
-        # grid.py:238-277 has no caller anywhere in the reference: out of the hot path.
-        raise NotImplementedError("grad_total_variation is outside the hot path (SURVEY.md section 8)")
+    @torch.no_grad()
+    def grad_total_variation(self, weight=1e-7, inputs=None, bound=1, B=1000000):
+        """grid.py:238-277: add the total-variation gradient at `inputs` (in [-bound, bound]; B random points when None)
+        to `embeddings.grad`.  Call after loss.backward() and before optimizer.step()."""
+        if inputs is None:
+            inputs = torch.rand(B, self.input_dim, device=self.embeddings.device)
+        else:
+            inputs = ((inputs + bound) / (2 * bound)).view(-1, self.input_dim)
+            B = inputs.shape[0]
+        if self.embeddings.grad is None:
+            raise ValueError("grad is None, should be called after loss.backward() and before optimizer.step()!")
+        L = self.offsets.shape[0] - 1
+        _backend.grad_total_variation(inputs.to(self.embeddings.dtype).contiguous(), self.embeddings, self.embeddings.grad,
+                                      self.offsets, weight, B, self.input_dim, self.embeddings.shape[1], L,
+                                      float(np.log2(self.per_level_scale)), self.base_resolution, self.gridtype_id,
+                                      self.align_corners)
 
 
 __all__ = ["grid_encode", "GridEncoder", "level_offsets"]

@@ -31,6 +31,8 @@ EXTS = {
     "_freqencoder": ("freqencoder", ["freqencoder.cu", "bindings.cpp"]),
     "_shencoder": ("shencoder", ["shencoder.cu", "bindings.cpp"]),
     "_ffmlp": ("ffmlp", ["ffmlp.cu", "bindings.cpp"]),
+    # evaluation-side extension (extern/chamfer3D): absolute source dir instead of lidarnerf/<sub>/src
+    "chamfer_3D": ("@extern/chamfer3D", ["chamfer3D.cu", "chamfer_cuda.cpp"]),
 }
 
 
@@ -53,7 +55,7 @@ def build(name):
     from torch.utils.cpp_extension import load
 
     sub, srcs = EXTS[name]
-    src_dir = os.path.join(REF, "lidarnerf", sub, "src")
+    src_dir = os.path.join(REF, sub[1:]) if sub.startswith("@") else os.path.join(REF, "lidarnerf", sub, "src")
     if not os.path.isdir(src_dir):
         print(f"[build_ref] {src_dir} not present (GPU box?) - skipping {name}")
         return False

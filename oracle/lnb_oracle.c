@@ -670,3 +670,129 @@ ORC_API void orc_adam_step(float *p, const float *g, float *m, float *v, size_t 
 ORC_API void orc_round_to_half(float *a, size_t n) {
     for (size_t i = 0; i < n; ++i) a[i] = to_half_precision(a[i]);
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * gridencoder.cu:695-808  kernel_grad_tv (fp32 tables; half tables are a no-op in the reference because its
+ * at::Half atomicAdd stub is empty, gridencoder.cu:27-31)
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_grad_total_variation(const float *inputs, const float *table, float *grad, const int32_t *offsets,
+                                      float weight, uint32_t B, uint32_t D, uint32_t C, uint32_t L, float S, uint32_t H,
+                                      uint32_t gridtype, int align_corners, const float *level_scales) {
+    for (uint32_t l = 0; l < L; ++l) {
+        const float *tab = table + (size_t)offsets[l] * C;
+        float *gt = grad + (size_t)offsets[l] * C;
+        const uint32_t hsize = (uint32_t)(offsets[l + 1] - offsets[l]);
+        const float scale = level_scales ? level_scales[l] : fmaf(exp2f((float)l * S), (float)H, -1.0f);
+        const uint32_t res = (uint32_t)ceilf(scale) + 1;
+        const float w = weight / (float)(2 * D);                                     /* :757 */
+        for (uint32_t b = 0; b < B; ++b) {
+            const float *x = inputs + (size_t)b * D;
+            int oob = 0;
+            uint32_t pg[8];
+            for (uint32_t d = 0; d < D; ++d) {
+                if (x[d] < 0 || x[d] > 1) oob = 1;
+                pg[d] = (uint32_t)floorf(fmaf(x[d], scale, align_corners ? 0.0f : 0.5f));   /* :739-741, nvcc contracts */
+            }
+            if (oob) continue;
+            const uint32_t index = grid_row(pg, D, gridtype, align_corners, hsize, res) * C;
+            for (uint32_t c = 0; c < C; ++c) {
+                float results = 0.f, idelta = 0.f;
+                for (uint32_t d = 0; d < D; ++d) {
+                    const uint32_t cur = pg[d];
+                    if (cur < res) {                                                   /* right neighbour :764-779 */
+                        pg[d] = cur + 1;
+                        const float gv = tab[index + c] - tab[grid_row(pg, D, gridtype, align_corners, hsize, res) * C + c];
+                        results += gv;
+                        idelta = fmaf(gv, gv, idelta);
+                    }
+                    if (cur > 0) {                                                     /* left neighbour :782-796 */
+                        pg[d] = cur - 1;
+                        const float gv = tab[index + c] - tab[grid_row(pg, D, gridtype, align_corners, hsize, res) * C + c];
+                        results += gv;
+                        idelta = fmaf(gv, gv, idelta);
+                    }
+                    pg[d] = cur;
+                }
+                gt[index + c] += w * results * (1.0f / sqrtf(idelta + 1e-9f));          /* :803-806 */
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * extern/chamfer3D/chamfer3D.cu:9-133  NmDistanceKernel: nearest neighbour of every xyz1 point in xyz2
+ * (squared distance, first minimum in index order)
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_chamfer_nn(const float *xyz1, const float *xyz2, uint32_t B, uint32_t N, uint32_t M, float *dist,
+                            int32_t *idx) {
+#pragma omp parallel for schedule(static) collapse(2)
+    for (uint32_t b = 0; b < B; ++b)
+        for (uint32_t j = 0; j < N; ++j) {
+            const float *p = xyz1 + ((size_t)b * N + j) * 3;
+            float best = 0.f;
+            int32_t best_i = 0;
+            for (uint32_t k = 0; k < M; ++k) {
+                const float *q = xyz2 + ((size_t)b * M + k) * 3;
+                const float x = q[0] - p[0], y = q[1] - p[1], z = q[2] - p[2];
+                /* x*x + y*y + z*z as nvcc 12.9 contracts it in the reference build (SASS of NmDistanceKernel:
+                 * FMUL y,y ; FFMA x,x,+ ; FFMA z,z,+): the y product is the one rounded on its own */
+                const float d = fmaf(z, z, fmaf(x, x, y * y));
+                if (k == 0 || d < best) { best = d; best_i = (int32_t)k; }
+            }
+            dist[(size_t)b * N + j] = best;
+            idx[(size_t)b * N + j] = best_i;
+        }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * lidarnerf/convert.py:99-160  lidar_to_pano_with_intensities: spherical projection with a z-buffer (the closest
+ * point of a pixel wins, the first one on ties).  fp32 arithmetic like numpy >= 2 evaluates the reference's
+ * expressions on float32 scalars; libm atan2f/sqrtf.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_lidar_to_pano(const float *points, uint32_t stride, uint32_t N, uint32_t H, uint32_t W, float fov_up,
+                               float fov, float max_depth, float *pano, float *intensities) {
+    const float pi = 3.14159265358979323846f;
+    const float fov_down = fov - fov_up;
+    const float down = (float)((double)fov_down / 180.0 * 3.14159265358979323846);
+    const float col_step = (float)(2.0 * 3.14159265358979323846 / (double)W);
+    const float row_step = (float)((double)fov / 180.0 * 3.14159265358979323846 / (double)H);
+    for (size_t i = 0; i < (size_t)H * W; ++i) pano[i] = 0.f, intensities[i] = 0.f;
+    for (uint32_t n = 0; n < N; ++n) {
+        const float *p = points + (size_t)n * stride;
+        const float x = p[0], y = p[1], z = p[2];
+        const float dist = sqrtf(x * x + y * y + z * z);
+        if (dist >= max_depth) continue;
+        const float beta = pi - atan2f(y, x);
+        const float alpha = atan2f(z, sqrtf(x * x + y * y)) + down;
+        const long c = lrintf(beta / col_step);                    /* round half to even, like Python's round() */
+        const long r = lrintf((float)H - alpha / row_step);
+        if (r >= (long)H || r < 0 || c >= (long)W || c < 0) continue;
+        float *px = pano + (size_t)r * W + c;
+        if (*px == 0.0f || *px > dist) {
+            *px = dist;
+            intensities[(size_t)r * W + c] = stride > 3 ? p[3] : 0.f;
+        }
+    }
+}
+
+/* lidarnerf/convert.py:194-235  pano_to_lidar_with_intensities: every non-empty pixel -> a point along its beam
+ * direction, in row-major pixel order.  Returns the number of points written to out [H*W,4]. */
+ORC_API uint32_t orc_pano_to_lidar(const float *pano, const float *intensities, uint32_t H, uint32_t W, float fov_up,
+                                   float fov, float *out) {
+    uint32_t n = 0;
+    const float pi = 3.14159265358979323846f;
+    for (uint32_t j = 0; j < H; ++j)
+        for (uint32_t i = 0; i < W; ++i) {
+            const float d = pano[(size_t)j * W + i];
+            if (d == 0.0f) continue;
+            /* numpy: float32 arrays combined with Python scalars stay float32 (evaluation order as written) */
+            const float beta = -((float)i - (float)W / 2.0f) / (float)W * 2.0f * pi;
+            const float alpha = (fov_up - (float)j / (float)H * fov) / 180.0f * pi;
+            out[(size_t)n * 4 + 0] = cosf(alpha) * cosf(beta) * d;
+            out[(size_t)n * 4 + 1] = cosf(alpha) * sinf(beta) * d;
+            out[(size_t)n * 4 + 2] = sinf(alpha) * d;
+            out[(size_t)n * 4 + 3] = intensities ? intensities[(size_t)j * W + i] : 0.f;
+            ++n;
+        }
+    return n;
+}

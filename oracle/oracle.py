@@ -282,3 +282,48 @@ def trunc_exp_forward(x):
 
 def trunc_exp_backward(g, x):
     return np.asarray(g, np.float32) * np.exp(np.clip(np.asarray(x, np.float32), -15, 15))
+
+
+def grad_total_variation(inputs, table, grad, offsets, weight, per_level_scale, base_resolution, gridtype=0,
+                         align_corners=False, level_scales=None):
+    """gridencoder.cu:695-808 (fp32): returns grad + TV gradient."""
+    x, t, off = _f(inputs), _f(table), _i(offsets)
+    g = _f(grad).copy()
+    B, D = x.shape
+    S = np.float32(np.log2(per_level_scale))
+    lib().orc_grad_total_variation(_p(x), _p(t), _p(g), _p(off), f32(weight), u32(B), u32(D), u32(t.shape[1]),
+                                   u32(off.shape[0] - 1), f32(S), u32(base_resolution), u32(gridtype),
+                                   i32(int(align_corners)), _p(None if level_scales is None else _f(level_scales)))
+    return g
+
+
+def chamfer_forward(xyz1, xyz2):
+    """extern/chamfer3D/chamfer3D.cu:135-166: (dist1 [B,N], dist2 [B,M], idx1, idx2)."""
+    a, b = _f(xyz1), _f(xyz2)
+    Bn, N, _ = a.shape
+    M = b.shape[1]
+    d1, i1 = np.empty((Bn, N), np.float32), np.empty((Bn, N), np.int32)
+    d2, i2 = np.empty((Bn, M), np.float32), np.empty((Bn, M), np.int32)
+    lib().orc_chamfer_nn(_p(a), _p(b), u32(Bn), u32(N), u32(M), _p(d1), _p(i1))
+    lib().orc_chamfer_nn(_p(b), _p(a), u32(Bn), u32(M), u32(N), _p(d2), _p(i2))
+    return d1, d2, i1, i2
+
+
+def lidar_to_pano_with_intensities(points, H, W, lidar_K, max_depth=80):
+    """convert.py:99-160: points [N,4] (or [N,3]) -> (pano [H,W], intensities [H,W])."""
+    p = _f(points)
+    pano, inten = np.empty((H, W), np.float32), np.empty((H, W), np.float32)
+    lib().orc_lidar_to_pano(_p(p), u32(p.shape[1]), u32(p.shape[0]), u32(H), u32(W), f32(lidar_K[0]), f32(lidar_K[1]),
+                            f32(max_depth), _p(pano), _p(inten))
+    return pano, inten
+
+
+def pano_to_lidar_with_intensities(pano, intensities, lidar_K):
+    """convert.py:194-235: -> points [n,4] in row-major order of the non-empty pixels."""
+    pa = _f(pano)
+    H, W = pa.shape
+    out = np.empty((H * W, 4), np.float32)
+    lib().orc_pano_to_lidar.restype = C.c_uint32
+    n = lib().orc_pano_to_lidar(_p(pa), _p(None if intensities is None else _f(intensities)), u32(H), u32(W),
+                                f32(lidar_K[0]), f32(lidar_K[1]), _p(out))
+    return out[:int(n)].copy()

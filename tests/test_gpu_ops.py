@@ -69,6 +69,9 @@ MARCH = [
     dict(seed=14, N=128, cascade=1, bound=1.0, fill=0.9, lidar=False, dt_gamma=1.0 / 128, max_steps=64),
     dict(seed=17, N=33, cascade=2, bound=2.0, fill=0.0, lidar=False, dt_gamma=0.0, max_steps=256),   # empty grid
     dict(seed=18, N=65, cascade=1, bound=1.0, fill=1.0, lidar=False, dt_gamma=0.0, max_steps=300),   # full grid
+    # > 32 emitting 32-candidate windows per ray: the counting pass' window log overflows, the emitting pass re-marches
+    dict(seed=21, N=48, cascade=1, bound=1.0, fill=0.4, lidar=False, dt_gamma=0.0, max_steps=4096),
+    dict(seed=22, N=40, cascade=2, bound=2.0, fill=0.5, lidar=False, dt_gamma=1.0 / 256, max_steps=2048),
 ]
 
 
