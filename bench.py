@@ -113,7 +113,7 @@ def make_pool(seq, n_rays, n_batches, seed, device):
     pool = []
     for b in range(n_batches):
         ro, rd, gt = seq.sample_batch(n_rays, frame=b % seq.n_frames, generator=gen, device=device)
-        pool.append(torch.cat([ro, rd, gt], dim=1).contiguous())     # [N, 9]: one buffer per batch
+        pool.append(torch.stack([ro, rd, gt], dim=0).contiguous())   # [3, N, 3]: one buffer per batch
     return pool
 
 
@@ -206,9 +206,7 @@ def main():
     pool_host = [b.cpu().pin_memory() for b in pool]
 
     def load(b):
-        eng.rays_o.copy_(b[:, 0:3], non_blocking=True)
-        eng.rays_d.copy_(b[:, 3:6], non_blocking=True)
-        eng.gt.copy_(b[:, 6:9], non_blocking=True)
+        eng.set_batch_packed(b)          # one copy: device pool (value) or pinned host memory (e2e)
 
     # ---- untimed preparation: size the sample budget from real counts, refresh the grid once, capture the graph ----
     cfg_interval = cfg.grid_update_interval
@@ -243,13 +241,8 @@ def main():
     losses = []
 
     def run(steps, host):
-        staging = torch.empty(N, 9, device=dev)
         for i in range(steps):
-            if host:
-                staging.copy_(pool_host[i % len(pool_host)], non_blocking=True)
-                load(staging)
-            else:
-                load(pool[i % len(pool)])
+            load(pool_host[i % len(pool_host)] if host else pool[i % len(pool)])
             eng.train_step(use_graph=not args.no_graph)
             if host:
                 # D2H read of the step's loss, every step: copied to pinned memory behind the step and consumed on the
@@ -468,7 +461,8 @@ def profile_kernels(eng, pool, load, iters=5):
     c = eng.cfg
     per_sample_fwd = c.num_levels * 8 * c.level_dim * 2                   # 512 B: L x 2^D corners x F x fp16
     alg = {
-        "lnb_adam_step": (eng.n_params * 34, "34 B/param: p,g,m,v read (16) + p,m,v,g=0 write (16) + fp16 shadow (2)"),
+        "lnb_adam_step": ((eng.n_params * 30, "30 B/param: p,g,m,v read (16) + p,m,v write (12) + fp16 shadow (2)") if c.late_grad_zero
+                          else (eng.n_params * 34, "34 B/param: p,g,m,v read (16) + p,m,v,g=0 write (16) + fp16 shadow (2)")),
         "lnb_grid_encode_forward_ex": (rows * (per_sample_fwd + 12 + c.num_levels * c.level_dim * 2),
                                        "SURVEY 8(d): per sample 512 B gathers + 12 B xyz + 64 B features out (the 27 MB "
                                        "table is L2-resident: DRAM traffic is far below this, see `traffic`)"),

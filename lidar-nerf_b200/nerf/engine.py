@@ -140,9 +140,10 @@ class LidarFieldEngine:
         # ---- static per-ray buffers ------------------------------------------------------------------------
         N = self.N
         f = dict(dtype=torch.float32, device=dev)
-        self.rays_o = torch.zeros(N, 3, **f)
-        self.rays_d = torch.zeros(N, 3, **f)
-        self.gt = torch.zeros(N, 3, **f)
+        # one buffer for the step's inputs, [3, N, 3] = (rays_o | rays_d | gt): a batch prepared in this layout on the
+        # host arrives with ONE copy (set_batch_packed); the three views are what the kernels read
+        self.batch = torch.zeros(3, N, 3, **f)
+        self.rays_o, self.rays_d, self.gt = self.batch[0], self.batch[1], self.batch[2]
         self.nears = torch.full((N,), c.min_near_lidar, **f)
         self.fars = self.nears * c.far_factor
         self.noises = torch.zeros(N, **f)
@@ -398,6 +399,10 @@ class LidarFieldEngine:
         self.rays_o.copy_(rays_o.reshape(-1, 3), non_blocking=True)
         self.rays_d.copy_(rays_d.reshape(-1, 3), non_blocking=True)
         self.gt.copy_(gt.reshape(-1, 3), non_blocking=True)
+
+    def set_batch_packed(self, batch):
+        """[3, N, 3] tensor (rays_o | rays_d | gt), device or pinned host memory -> static buffers, one async copy."""
+        self.batch.copy_(batch, non_blocking=True)
 
     def train_step(self, use_graph=True):
         """One optimiser step on the batch currently in the static buffers.  In graph mode on one rank the update is
