@@ -199,6 +199,8 @@ def main():
         cfg.late_grad_zero = False
     if os.environ.get("LNB_PIPELINE_ADAM") == "0":
         cfg.pipeline_adam = False
+    if os.environ.get("LNB_OVERLAP_EXCHANGE") == "0":
+        cfg.overlap_exchange = False
     seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
     eng = LidarFieldEngine(cfg, N, device=dev, sample_budget=N * 64)
     eng.seed_occupancy_from_points(seq.surface_points())
@@ -305,7 +307,9 @@ def main():
                           "samples_per_ray": produced / N, "sample_budget_M": eng.M, "params": eng.n_params,
                           "grid_refresh_ms": refresh_ms, "grid_refresh_every": cfg_interval,
                           "l2": "each step streams the 383 MB Adam state (> 126 MB L2); no explicit flush",
-                          "parallelism": f"dp{world} (NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params)" if world > 1 else "single"},
+                          "parallelism": (f"dp{world} (NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params"
+                                          + (", overlapped with the next step's march)" if cfg.overlap_exchange else ")"))
+                          if world > 1 else "single"},
                "clocks": clk,
                "e2e": {"value": world * N * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                        "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4,

@@ -63,6 +63,7 @@ class FieldConfig:
     fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
     compact_backward: bool = True        # backward kernels walk only the samples up to each ray's early stop
     late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam
+    overlap_exchange: bool = True        # data parallel, graph mode: the exchange overlaps the next step's march
     pipeline_adam: bool = False          # graph mode, one rank: Adam of step i runs next to the march of step i+1
                                          # (measured: -6 us/step device time, +CPU launch work; off by default)
     seed: int = 0
@@ -176,6 +177,8 @@ class LidarFieldEngine:
         self.M = 0
         self._graph = None
         self._side = torch.cuda.Stream(device=dev)     # side branch of the step (per-ray direction terms)
+        self._comm = torch.cuda.Stream(device=dev)     # data parallel: gradient exchange + sharded Adam
+        self._graph_b = None
         self._alloc_samples(sample_budget or N * 64)
 
     # ------------------------------------------------------------------------------------------------------
@@ -216,6 +219,12 @@ class LidarFieldEngine:
     # ------------------------------------------------------------------------------------------------------
     def _forward_backward(self):
         """Everything between 'rays are in the static buffers' and 'flat gradient is complete'."""
+        self._fb_march()
+        self._fb_field()
+
+    def _fb_march(self):
+        """The part of the step that does not read parameters: jitter noise and the occupancy march of the batch.  (The
+        data-parallel step runs it next to the previous step's gradient exchange.)"""
         c, N, M, s = self.cfg, self.N, self.M, self._s()
         p = lambda t: vp(t.data_ptr())   # noqa: E731
         self.counter.zero_()
@@ -227,26 +236,30 @@ class LidarFieldEngine:
             # march start per ray, for the absolute-depth term of the loss (raymarching.cu:375)
             torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
             torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
-        if self.fused:
-            # per-ray direction terms depend only on rays_d and the head weights: a side branch next to the march
-            main = torch.cuda.current_stream()
-            self._side.wait_stream(main)
-            with torch.cuda.stream(self._side):
-                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
-                                            u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
-                    "ray_terms")
-
         _ck(lib.lnb_march_rays_train_ex(p(self.rays_o), p(self.rays_d), p(self.bitfield), f32(c.bound), f32(c.dt_gamma),
                                         u32(c.max_steps), u32(N), u32(c.cascade), u32(c.grid_size), u32(M),
                                         p(self.nears), p(self.fars), p(self.xyzs),
                                         p(self.dirs) if self.dirs is not None else vp(0), p(self.deltas), p(self.rays),
                                         p(self.counter), p(self.noises), p(self.ray_ids), s), "march_rays_train")
+
+    def _fb_field(self):
+        """Encoding, field network, compositing + loss, backward: everything that reads parameters."""
+        c, N, M, s = self.cfg, self.N, self.M, self._s()
+        p = lambda t: vp(t.data_ptr())   # noqa: E731
+        main = torch.cuda.current_stream()
+        if self.fused:
+            # per-ray direction terms depend only on rays_d and the head weights: a side branch next to the gather
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
+                                            u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
+                    "ray_terms")
         # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
         # (the extended march also zeroes the padding rows of the last tile)
         na = p(self.counter)
-        if self.fused or self._in_graph_body:
-            torch.cuda.current_stream().wait_stream(self._side)    # join: ray terms (and the pipelined Adam) are done
+        if self._in_graph_body and self._pipelined:
+            main.wait_stream(self._side)               # the pipelined Adam (same side stream) must be done before the gather
         compact = bool(c.compact_backward and c.fused_composite and self.fused)
         nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
@@ -254,6 +267,7 @@ class LidarFieldEngine:
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
             "grid_fwd")
         if self.fused:
+            main.wait_stream(self._side)               # join: ray terms ready
             _ck(lib.lnb_field_forward(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
                                       p(self.ray_bias), u32(M), u32(self.enc_dim), u32(c.sigma_layers),
                                       u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim),
@@ -363,10 +377,13 @@ class LidarFieldEngine:
         self.ex.all_gather(self.Ph, self.Ph_shard)
 
     def flush(self):
-        """Apply the update the pipelined graph step still owes (the gradient of the last step).  Call before reading
-        the parameters, refreshing the density grid, or mixing in eager steps; a no-op when nothing is pending."""
+        """Settle what the asynchronous step schedules still owe: the update of the pipelined graph step (the gradient of
+        the last step) and, data parallel, the gradient exchange running on the communication stream.  Call before
+        reading the parameters, refreshing the density grid, or mixing in eager steps; cheap when nothing is pending."""
         if self._pending:
             self._optimizer()
+        if self.ex.world > 1:
+            torch.cuda.current_stream().wait_stream(self._comm)
 
     def _set_hyper(self, enable, lr=None):
         c = self.cfg
@@ -422,6 +439,22 @@ class LidarFieldEngine:
                 self.flush()              # the refresh evaluates the network: it needs this step's update
                 self.update_density_grid()
             return
+        if use_graph and self.ex.world > 1 and self.cfg.overlap_exchange:
+            # data parallel: [march of THIS batch] runs while the previous step's gradient exchange is still in flight on
+            # the communication stream; the rest of the step waits for the all-gathered parameters
+            if self._graph is None:
+                self._capture()
+            main = torch.cuda.current_stream()
+            self._graph.replay()                        # graph A: noise + march (reads no parameters)
+            main.wait_stream(self._comm)
+            self._graph_b.replay()                      # graph B: gather ... scatter
+            self._comm.wait_stream(main)
+            with torch.cuda.stream(self._comm):
+                self._optimizer()                       # reduce-scatter -> Adam on the shard -> all-gather
+            if interval > 0 and self.step_count % interval == 0:
+                main.wait_stream(self._comm)
+                self.update_density_grid()
+            return
         self.flush()
         if use_graph:
             if self._graph is None:
@@ -445,8 +478,16 @@ class LidarFieldEngine:
             self.G.copy_(g_backup)
         torch.cuda.current_stream().wait_stream(side)
         torch.cuda.synchronize(self.dev)
-        g = torch.cuda.CUDAGraph()
         # thread_local: other threads (e.g. NCCL's watchdog) may legally touch the CUDA API during the capture
+        if self.ex.world > 1 and self.cfg.overlap_exchange:
+            ga, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga, capture_error_mode="thread_local"):
+                self._fb_march()
+            with torch.cuda.graph(gb, capture_error_mode="thread_local"):
+                self._fb_field()
+            self._graph, self._graph_b = ga, gb
+            return
+        g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g, capture_error_mode="thread_local"):
             self._graph_body()
         self._graph = g
@@ -543,6 +584,8 @@ class LidarFieldEngine:
         with the LiDAR prior grid (cells a GT return falls into stay occupied)."""
         from ..raymarching import packbits
         c = self.cfg
+        if self.ex.world > 1:
+            torch.cuda.current_stream().wait_stream(self._comm)   # the network is evaluated: parameters must be settled
         H3 = c.grid_size ** 3
         n_updates = self.step_count // max(c.grid_update_interval, 1)
         full = (n_updates <= 16) if full is None else full
