@@ -201,6 +201,8 @@ def main():
         cfg.pipeline_adam = False
     if os.environ.get("LNB_OVERLAP_EXCHANGE") == "0":
         cfg.overlap_exchange = False
+    if os.environ.get("LNB_FUSED_EXCHANGE") == "0":
+        cfg.fused_exchange = False
     seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
     eng = LidarFieldEngine(cfg, N, device=dev, sample_budget=N * 64)
     eng.seed_occupancy_from_points(seq.surface_points())
@@ -307,7 +309,9 @@ def main():
                           "samples_per_ray": produced / N, "sample_budget_M": eng.M, "params": eng.n_params,
                           "grid_refresh_ms": refresh_ms, "grid_refresh_every": cfg_interval,
                           "l2": "each step streams the 383 MB Adam state (> 126 MB L2); no explicit flush",
-                          "parallelism": (f"dp{world} (NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params"
+                          "parallelism": (f"dp{world} (" + ("ONE peer-memory kernel over NVLink: reduce-scatter fp32 grad + sharded Adam + "
+                                                          "all-gather fp16 params" if eng._peer is not None else
+                                                          "NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params")
                                           + (", overlapped with the next step's march)" if cfg.overlap_exchange else ")"))
                           if world > 1 else "single"},
                "clocks": clk,

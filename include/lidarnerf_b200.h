@@ -259,6 +259,16 @@ int lnb_adam_step(float *params, float *grad, float *exp_avg, float *exp_avg_sq,
  * before each replay); enable == 0 turns the captured update into a no-op (nothing pending). */
 int lnb_adam_set_hyper(float *hyper_dev, float lr, float bias_correction1, float bias_correction2, float grad_scale,
                        int enable, lnb_stream_t stream);
+/* Data-parallel exchange fused with the optimiser over NVLink peer memory (SURVEY.md 8e "better variant"): this rank
+ * sums shard [shard_lo, shard_lo + shard_n) of the flat fp32 gradient straight out of the `world` gradient buffers
+ * grad_ptrs[q] (peer-mapped device pointers, rank order), runs Adam on its shard (params/exp_avg/exp_avg_sq hold only
+ * the shard) and stores the updated fp16 parameters into every rank's shadow half_ptrs[q].  grad_ptrs / half_ptrs are
+ * HOST arrays of `world` <= 16 pointers.  The caller provides the cross-rank barriers: every rank's gradient complete
+ * before the launch, every rank's launch complete before the shadows are read. */
+int lnb_dp_adam_exchange(const void *const *grad_ptrs, void *const *half_ptrs, uint32_t world, float *params_shard,
+                         float *exp_avg_shard, float *exp_avg_sq_shard, size_t shard_lo, size_t shard_n, float lr,
+                         float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
+                         float grad_scale, lnb_stream_t stream);
 int lnb_adam_step_dev(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half, size_t n,
                       float beta1, float beta2, float eps, const float *hyper_dev, int zero_grad, lnb_stream_t stream);
 

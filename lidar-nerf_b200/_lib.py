@@ -39,7 +39,7 @@ SYMBOLS = [
     "lnb_freq_encode_forward", "lnb_freq_encode_backward",
     "lnb_sh_encode_forward", "lnb_sh_encode_backward",
     "lnb_ffmlp_forward", "lnb_ffmlp_inference", "lnb_ffmlp_backward_workspace_bytes", "lnb_ffmlp_backward",
-    "lnb_allocate_splitk", "lnb_free_splitk", "lnb_adam_step", "lnb_adam_set_hyper", "lnb_adam_step_dev",
+    "lnb_allocate_splitk", "lnb_free_splitk", "lnb_adam_step", "lnb_adam_set_hyper", "lnb_adam_step_dev", "lnb_dp_adam_exchange",
     "lnb_grid_encode_forward_ex", "lnb_grid_encode_backward_ex", "lnb_ffmlp_backward_accumulate", "lnb_ffmlp_forward_ex",
     "lnb_march_rays_train_ex", "lnb_zero_sample_tail_ex", "lnb_field_supported", "lnb_field_ray_terms",
     "lnb_field_forward", "lnb_field_head_backward",

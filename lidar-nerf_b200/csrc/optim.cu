@@ -68,6 +68,55 @@ k_adam(float *__restrict__ p, float *__restrict__ g, float *__restrict__ m, floa
     }
 }
 
+// ----------------------------------------------------------------------------------------------------------------
+// Data-parallel exchange fused with the optimiser, over NVLink peer memory (no NCCL on the data path):
+//   reduce-scatter  : this rank sums ITS shard of the flat gradient straight out of every rank's gradient buffer
+//                     (peer loads over NVLink / NVSwitch, fixed rank order -> every rank computes bit-identical sums),
+//   Adam            : fp32 master weights and moments of the shard live only on this rank,
+//   all-gather      : the updated fp16 parameters are stored straight into every rank's parameter shadow (peer stores).
+// One streaming pass; the transfers overlap the arithmetic element by element.  The caller brackets the launch with two
+// cross-rank barriers (all gradients complete before / all shadows complete after) - torch symmetric memory provides
+// both the peer mappings and the device-side barriers.
+// ----------------------------------------------------------------------------------------------------------------
+constexpr int kMaxPeers = 16;
+struct PeerPtrs {
+    const float *grad[kMaxPeers];
+    __half *half[kMaxPeers];
+};
+
+__global__ void __launch_bounds__(kThreads)
+k_dp_adam_exchange(PeerPtrs pp, uint32_t world, float *__restrict__ p, float *__restrict__ m, float *__restrict__ v,
+                   size_t lo, size_t n, AdamArgs a) {
+    const size_t n4 = n / 4;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float4 *p4 = reinterpret_cast<float4 *>(p), *m4 = reinterpret_cast<float4 *>(m), *v4 = reinterpret_cast<float4 *>(v);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+        float4 gq[kMaxPeers];
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)        // all peer loads in flight before the first use
+            if (q < (int)world) gq[q] = __ldcv(reinterpret_cast<const float4 *>(pp.grad[q] + lo) + i);
+        float4 gg = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < (int)world) gg.x += gq[q].x, gg.y += gq[q].y, gg.z += gq[q].z, gg.w += gq[q].w;
+        float4 pq = p4[i], mm = m4[i], vv = v4[i];
+        adam_one(pq.x, gg.x, mm.x, vv.x, a);
+        adam_one(pq.y, gg.y, mm.y, vv.y, a);
+        adam_one(pq.z, gg.z, mm.z, vv.z, a);
+        adam_one(pq.w, gg.w, mm.w, vv.w, a);
+        p4[i] = pq;
+        m4[i] = mm;
+        v4[i] = vv;
+        __half2 h0 = __floats2half2_rn(pq.x, pq.y), h1 = __floats2half2_rn(pq.z, pq.w);
+        uint2 packed;
+        packed.x = *reinterpret_cast<unsigned *>(&h0);
+        packed.y = *reinterpret_cast<unsigned *>(&h1);
+#pragma unroll
+        for (int q = 0; q < kMaxPeers; ++q)
+            if (q < (int)world) reinterpret_cast<uint2 *>(pp.half[q] + lo)[i] = packed;
+    }
+}
+
 __global__ void k_adam_set_hyper(float *hyper, float lr, float inv_bc1, float inv_sqrt_bc2, float gscale, float enable) {
     hyper[0] = lr, hyper[1] = inv_bc1, hyper[2] = inv_sqrt_bc2, hyper[3] = gscale, hyper[4] = enable;
 }
@@ -124,4 +173,28 @@ extern "C" int lnb_adam_step(float *params, float *grad, float *exp_avg, float *
     if (bias_correction1 == 0.f || bias_correction2 <= 0.f) return LNB_ERR_INVALID_ARGUMENT;
     AdamArgs a{lr, beta1, beta2, eps, 1.f / bias_correction1, 1.f / sqrtf(bias_correction2), grad_scale};
     return launch_adam(params, grad, exp_avg, exp_avg_sq, params_half, n, a, nullptr, zero_grad, as_stream(stream));
+}
+
+extern "C" int lnb_dp_adam_exchange(const void *const *grad_ptrs, void *const *half_ptrs, uint32_t world,
+                                    float *params_shard, float *exp_avg_shard, float *exp_avg_sq_shard, size_t shard_lo,
+                                    size_t shard_n, float lr, float beta1, float beta2, float eps, float bias_correction1,
+                                    float bias_correction2, float grad_scale, lnb_stream_t stream) {
+    if (!grad_ptrs || !half_ptrs || !params_shard || !exp_avg_shard || !exp_avg_sq_shard) return LNB_ERR_INVALID_ARGUMENT;
+    if (world < 1 || world > (uint32_t)kMaxPeers) return LNB_ERR_UNSUPPORTED;
+    if (shard_n % 4 != 0 || shard_lo % 4 != 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (bias_correction1 == 0.f || bias_correction2 <= 0.f) return LNB_ERR_INVALID_ARGUMENT;
+    PeerPtrs pp = {};
+    for (uint32_t q = 0; q < world; ++q) {
+        if (!grad_ptrs[q] || !half_ptrs[q]) return LNB_ERR_INVALID_ARGUMENT;
+        pp.grad[q] = static_cast<const float *>(grad_ptrs[q]);
+        pp.half[q] = static_cast<__half *>(half_ptrs[q]);
+    }
+    if (shard_n == 0) return LNB_OK;
+    AdamArgs a{lr, beta1, beta2, eps, 1.f / bias_correction1, 1.f / sqrtf(bias_correction2), grad_scale};
+    const size_t want = (shard_n / 4 + kThreads - 1) / kThreads;
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    k_dp_adam_exchange<<<blocks, kThreads, 0, as_stream(stream)>>>(pp, world, params_shard, exp_avg_shard, exp_avg_sq_shard,
+                                                                  shard_lo, shard_n, a);
+    count_launch();
+    return launch_status();
 }

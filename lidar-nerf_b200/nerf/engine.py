@@ -11,6 +11,7 @@ What it replaces in the reference (SURVEY.md sections 3.1-3.2): `Trainer.train_s
 Parameters live in ONE flat fp32 vector [hash table | density-MLP weights | LiDAR-head weights] with a flat
 fp16 shadow the kernels read, so Adam and the data-parallel gradient exchange are single passes over one buffer.
 """
+import ctypes as C
 import math
 from dataclasses import dataclass
 
@@ -63,6 +64,8 @@ class FieldConfig:
     fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
     compact_backward: bool = True        # backward kernels walk only the samples up to each ray's early stop
     late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam
+    fused_exchange: bool = True          # data parallel: one peer-memory kernel (reduce-scatter + Adam + all-gather) over
+                                         # NVLink via torch symmetric memory; falls back to NCCL when it cannot be set up
     overlap_exchange: bool = True        # data parallel, graph mode: the exchange overlaps the next step's march
     pipeline_adam: bool = False          # graph mode, one rank: Adam of step i runs next to the march of step i+1
                                          # (measured: -6 us/step device time, +CPU launch work; off by default)
@@ -113,6 +116,29 @@ class LidarFieldEngine:
         P[n_table:n].uniform_(-bound_w, bound_w, generator=gen)
         self.G = torch.zeros(npad, dtype=torch.float32, device=dev)
         self.Ph = P.to(dev).to(torch.float16)
+        self._peer = None
+        if self.ex.world > 1 and c.fused_exchange:
+            # gradient and fp16 shadow in symmetric (peer-mapped) memory: the exchange becomes ONE kernel that reads every
+            # rank's gradient shard and writes every rank's shadow over NVLink (lnb_dp_adam_exchange); NCCL otherwise
+            try:
+                import torch.distributed as dist
+                import torch.distributed._symmetric_memory as symm
+                Gs = symm.empty(npad, dtype=torch.float32, device=dev)
+                hG = symm.rendezvous(Gs, dist.group.WORLD)
+                Ps = symm.empty(npad, dtype=torch.float16, device=dev)
+                hP = symm.rendezvous(Ps, dist.group.WORLD)
+                Gs.zero_()
+                Ps.copy_(self.Ph)
+                ptr_t = C.c_void_p * self.ex.world
+                self._peer = dict(hG=hG, hP=hP, g=ptr_t(*[int(x) for x in hG.buffer_ptrs]),
+                                  h=ptr_t(*[int(x) for x in hP.buffer_ptrs]))
+                self.G, self.Ph = Gs, Ps
+                torch.cuda.synchronize(dev)
+                hG.barrier(channel=0, timeout_ms=20000)        # every rank's buffers are initialised
+            except Exception as e:     # noqa: BLE001 - any failure of the peer mapping: keep the NCCL exchange
+                if self.ex.rank == 0:
+                    print(f"[lidar-nerf_b200] symmetric memory unavailable ({type(e).__name__}: {e}); NCCL exchange")
+                self._peer = None
         if self.ex.world > 1:
             # fp32 master weights and Adam moments exist only for this rank's shard (1/world of 3 x 54.8 MB)
             self.P = P[self.ex.lo:self.ex.hi].to(dev)
@@ -368,6 +394,19 @@ class LidarFieldEngine:
         if self.ex.world == 1:
             adam_step(self.P, self.G, self.m, self.v, self.Ph, lr, c.beta1, c.beta2, c.eps, self.step_count,
                       grad_scale=1.0 / c.loss_scale, zero_grad=not c.late_grad_zero)
+            return
+        if self._peer is not None:
+            # all ranks' gradients complete -> [peer reduce-scatter + Adam + peer all-gather] -> all shadows complete
+            pr = self._peer
+            pr["hG"].barrier(channel=0, timeout_ms=20000)
+            _ck(lib.lnb_dp_adam_exchange(pr["g"], pr["h"], u32(self.ex.world), vp(self.P.data_ptr()),
+                                         vp(self.m.data_ptr()), vp(self.v.data_ptr()), sz(self.ex.lo), sz(self.ex.shard),
+                                         f32(lr), f32(c.beta1), f32(c.beta2), f32(c.eps),
+                                         f32(1.0 - c.beta1 ** self.step_count), f32(1.0 - c.beta2 ** self.step_count),
+                                         f32(dp.grad_scale(c.loss_scale)), self._s()), "dp_adam_exchange")
+            pr["hG"].barrier(channel=1, timeout_ms=20000)
+            if not c.late_grad_zero:
+                self.G.zero_()
             return
         self.ex.reduce_scatter(self.G, self.G_shard)
         if not c.late_grad_zero:

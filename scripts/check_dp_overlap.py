@@ -17,9 +17,9 @@ dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
 seq = SyntheticLidarSequence(H=16, W=256, n_frames=2, device=dev)
 out = {}
-for overlap in (False, True):
+for overlap, fused in ((False, False), (True, False), (True, True)):
     cfg = FieldConfig(log2_hashmap_size=15, desired_resolution=2048, grid_update_interval=4, lr=5e-3, perturb=False,
-                      overlap_exchange=overlap)
+                      overlap_exchange=overlap, fused_exchange=fused)
     eng = LidarFieldEngine(cfg, 512, device=dev, sample_budget=512 * 128)
     eng.seed_occupancy_from_points(seq.surface_points())
     gen = torch.Generator().manual_seed(100 + rank)
@@ -30,16 +30,19 @@ for overlap in (False, True):
         eng.train_step(use_graph=True)
     eng.flush()
     torch.cuda.synchronize()
-    out[overlap] = (eng.Ph.clone().float(), eng.bitfield.clone(), eng.step_count)
-a, b = out[True], out[False]
-assert a[2] == b[2] == 11
-assert torch.equal(a[1], b[1]), "density-grid refreshes saw different parameters"
-rel = float((a[0] - b[0]).norm() / (b[0] - b[0].mean()).norm())
-assert rel < 2e-3, rel
-# every rank holds the same parameters
-ref = a[0].clone()
-dist.broadcast(ref, src=0)
-assert torch.equal(ref, a[0]), "ranks diverged"
-print(f"[rank {rank}] OK: overlapped == sequential (rel {rel:.2e}), ranks identical", flush=True)
+    out[(overlap, fused)] = (eng.Ph.clone().float(), eng.bitfield.clone(), eng.step_count, eng._peer is not None)
+    del eng
+b = out[(False, False)]
+for key in ((True, False), (True, True)):
+    a = out[key]
+    assert a[2] == b[2] == 11
+    assert torch.equal(a[1], b[1]), "density-grid refreshes saw different parameters"
+    rel = float((a[0] - b[0]).norm() / (b[0] - b[0].mean()).norm())
+    assert rel < 2e-3, (key, rel)
+    ref = a[0].clone()                   # every rank holds the same parameters
+    dist.broadcast(ref, src=0)
+    assert torch.equal(ref, a[0]), "ranks diverged"
+    print(f"[rank {rank}] OK overlap={key[0]} fused={key[1]} (peer memory in use: {a[3]}): == sequential NCCL schedule "
+          f"(rel {rel:.2e}), ranks identical", flush=True)
 dist.barrier()
 dist.destroy_process_group()
