@@ -1,7 +1,10 @@
 """Data-parallel plumbing of the training step: rays shard across ranks with no data-path
-collective; the ONE exchange per optimiser step is a sum all-reduce of the flat fp32 gradient (hash table + both
-MLPs, 54.8 MB) over NCCL/NVLink, with the 1/world mean folded into Adam's gradient scale.  Backend-agnostic
-(NCCL on GPUs, gloo in the CPU tests)."""
+collective; the ONE exchange per optimiser step is reduce-scatter(fp32 gradient) -> Adam on this rank's shard ->
+all-gather(fp16 parameters), with the 1/world mean folded into Adam's gradient scale.
+
+This module is the NCCL form of that exchange (and the layout both forms share); when torch symmetric memory is
+available the engine replaces the three calls by ONE peer-memory kernel over NVLink (lnb_dp_adam_exchange,
+nerf/engine.py).  Backend-agnostic (NCCL on GPUs, gloo in the CPU tests)."""
 import torch.distributed as dist
 
 

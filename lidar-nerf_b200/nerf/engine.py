@@ -1,7 +1,6 @@
 """Fused LiDAR-field training engine: one optimiser step of the reference's hot path
-(march -> hash-grid -> density MLP -> LiDAR head -> composite -> loss -> backward -> Adam) as ~17 launches of
-liblnb200.so kernels on one stream, captured in a CUDA graph, with no autograd, no host sync and no allocation
-inside the step.
+(march -> hash-grid -> density MLP -> LiDAR head -> composite -> loss -> backward -> Adam) as 9 launches of
+liblnb200.so kernels, captured in a CUDA graph, with no autograd, no host sync and no allocation inside the step.
 
 What it replaces in the reference (SURVEY.md sections 3.1-3.2): `Trainer.train_step` (nerf/utils.py:697-734) +
 `NeRFRenderer.run` (nerf/renderer.py:99-298) + `NeRFNetwork.density/color` (nerf/network.py:162-237) +
@@ -10,6 +9,15 @@ What it replaces in the reference (SURVEY.md sections 3.1-3.2): `Trainer.train_s
 
 Parameters live in ONE flat fp32 vector [hash table | density-MLP weights | LiDAR-head weights] with a flat
 fp16 shadow the kernels read, so Adam and the data-parallel gradient exchange are single passes over one buffer.
+
+The step, in launch order:
+  march (+ tail zeroing)  ||  per-ray direction terms        k_march_train, k_ray_dir_terms
+  hash-grid gather                                            k_grid_fwd
+  density MLP -> sigma/geo -> LiDAR head                      k_field_fwd            (tcgen05 + TMEM)
+  composite fwd + LiDAR loss + composite bwd + live-row list  k_lidar_composite_step
+  head backward / density-MLP backward on the live rows       k_mlp_bwd<head>, k_mlp_bwd   (tcgen05 + TMEM)
+  gradient-table memset, hash-grid scatter on the live rows   k_grid_bwd
+  Adam (one rank)  |  peer-memory reduce-scatter + Adam + all-gather (data parallel)   k_adam | k_dp_adam_exchange
 """
 import ctypes as C
 import math
