@@ -12,6 +12,8 @@ nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv > 
 if has micro; then
   ./scripts/micro/mma_shapes.bin > $OUT/mma_shapes.txt 2>&1
   cat $OUT/mma_shapes.txt
+  [ -x scripts/micro/gather_peak.bin ] && timeout 60 ./scripts/micro/gather_peak.bin > $OUT/gather_peak.txt 2>&1 && cat $OUT/gather_peak.txt
+  [ -x scripts/micro/tmem_ld.bin ] && timeout 60 ./scripts/micro/tmem_ld.bin > $OUT/tmem_ld.txt 2>&1 && cat $OUT/tmem_ld.txt
 fi
 if has tests; then
   ( time timeout 900 python -m pytest tests -m gpu -x -q ) > $OUT/pytest_gpu.log 2>&1
