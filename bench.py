@@ -310,7 +310,8 @@ def main():
                "config": {"workload": WORKLOAD, "rays_per_gpu": N, "samples_per_step": produced,
                           "samples_per_ray": produced / N, "sample_budget_M": eng.M, "params": eng.n_params,
                           "grid_refresh_ms": refresh_ms, "grid_refresh_every": cfg_interval,
-                          "l2": "each step streams the 383 MB Adam state (> 126 MB L2); no explicit flush",
+                          "l2": "no explicit flush: every step streams ~410 MB of Adam state, a 55 MB gradient memset and ~500 MB of saved "
+                                "activations (written, then read back) through the 126 MB L2, and draws a new ray batch",
                           "parallelism": (f"dp{world} (" + ("ONE peer-memory kernel over NVLink: reduce-scatter fp32 grad + sharded Adam + "
                                                           "all-gather fp16 params" if eng._peer is not None else
                                                           "NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params")
