@@ -80,3 +80,27 @@ def test_cpu_tensors_are_rejected_like_torch_check():
     x = torch.zeros(4, 3)
     with pytest.raises(RuntimeError, match="CUDA tensor"):
         be._freqencoder.freq_encode_forward(x, 4, 3, 2, 15, torch.zeros(4, 15))
+
+
+def test_header_is_plain_c_and_a_c_client_links_and_runs(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and as C++11 with -Werror, and a client written in C
+    (examples/capi_client.c: no Python, no torch) links against liblnb200.so and gets the documented status codes."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "lidarnerf_b200.h")
+    for lang, std in (("c", "-std=c99"), ("c++", "-std=c++11")):
+        r = subprocess.run([gcc, std, "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-x", lang, hdr],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+    libdir = os.path.join(ROOT, "lidar-nerf_b200", "lib")
+    exe = str(tmp_path / "capi_client")
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"),
+                        os.path.join(ROOT, "examples", "capi_client.c"), "-L", libdir, "-llnb200",
+                        f"-Wl,-rpath,{libdir}", "-o", exe], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "sm_100a" in r.stdout and "invalid argument" in r.stdout
