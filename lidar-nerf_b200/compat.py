@@ -6,6 +6,7 @@
   * this package's B2 modules under the top-level names the reference's factory imports
     (`from gridencoder import GridEncoder`, `from freqencoder import FreqEncoder`, `from shencoder import SHEncoder`,
     lidarnerf/encoding.py:68,73,78; plus `ffmlp` and `raymarching`),
+  * this package's tinycudann-free `NeRFNetwork` as `lidarnerf.nerf.network_tcnn` (imported by `main_lidarnerf.py --tcnn`),
 and, if the reference package `lidarnerf` is importable, fills the (empty) `lidarnerf.raymarching` namespace
 (lidarnerf/raymarching/__init__.py is 0 bytes while nerf/renderer.py:140 calls raymarching.near_far_from_aabb).
 """
@@ -19,6 +20,9 @@ def install(patch_lidarnerf=True):
     pkg = __name__.rsplit(".", 1)[0]
     for name in ("gridencoder", "freqencoder", "shencoder", "ffmlp", "raymarching"):
         sys.modules[name] = importlib.import_module(f"{pkg}.{name}")
+    # `--tcnn` / `-L` of the entry script imports lidarnerf.nerf.network_tcnn, whose reference version needs the
+    # uninstallable tinycudann: pre-register this library's class under that module path (main_lidarnerf.py:289-308)
+    sys.modules.setdefault("lidarnerf.nerf.network_tcnn", importlib.import_module(f"{pkg}.nerf.network_tcnn"))
     if patch_lidarnerf:
         try:
             ref_rm = importlib.import_module("lidarnerf.raymarching")

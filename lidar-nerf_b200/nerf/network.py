@@ -29,7 +29,8 @@ def _run_stack(layers, h):
 class NeRFNetwork(NeRFRenderer):
     def __init__(self, encoding="hashgrid", encoding_dir="frequency", multires=15, desired_resolution=2048,
                  log2_hashmap_size=19, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3,
-                 hidden_dim_color=64, out_color_dim=3, out_lidar_color_dim=2, bound=1, use_ffmlp=True, **kwargs):
+                 hidden_dim_color=64, out_color_dim=3, out_lidar_color_dim=2, bound=1, use_ffmlp=True, level_dim=2,
+                 **kwargs):
         super().__init__(bound, **kwargs)
         self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
         self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
@@ -40,7 +41,7 @@ class NeRFNetwork(NeRFRenderer):
             self.encoder, self.in_dim = get_encoder("frequency", multires=multires)
         else:
             self.encoder, self.in_dim = get_encoder(encoding, desired_resolution=desired_resolution,
-                                                    log2_hashmap_size=log2_hashmap_size)
+                                                    log2_hashmap_size=log2_hashmap_size, level_dim=level_dim)
         self.encoder_dir, self.in_dim_dir = get_encoder("sphere_harmonics")
         self.encoder_lidar_dir, self.in_dim_lidar_dir = get_encoder("frequency", multires=12)
         raw_rgb, raw_lidar = self.in_dim_dir + geo_feat_dim, self.in_dim_lidar_dir + geo_feat_dim

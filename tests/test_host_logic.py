@@ -180,3 +180,39 @@ def test_bench_product_arm_fails_loudly_without_a_gpu():
                        capture_output=True, text=True, timeout=300, cwd=root)
     assert r.returncode != 0
     assert not [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+
+
+def test_network_tcnn_module_path_without_tinycudann():
+    """`main_lidarnerf.py --tcnn` imports lidarnerf.nerf.network_tcnn.NeRFNetwork with the tcnn keyword set
+    (main_lidarnerf.py:289-308); this library serves that module path without tinycudann."""
+    import ast
+    import inspect
+    import sys
+    from lidar_nerf_b200 import compat
+    from lidar_nerf_b200.nerf import network_tcnn
+    ours = inspect.signature(network_tcnn.NeRFNetwork.__init__).parameters
+    ref_file = "/root/reference/lidarnerf/nerf/network_tcnn.py"
+    if os.path.exists(ref_file):       # build container only: every constructor keyword of the reference is accepted
+        tree = ast.parse(open(ref_file).read())
+        init = next(n for c in tree.body if isinstance(c, ast.ClassDef) and c.name == "NeRFNetwork"
+                    for n in c.body if isinstance(n, ast.FunctionDef) and n.name == "__init__")
+        for a, d in zip(init.args.args[1:], init.args.defaults):
+            assert a.arg in ours, a.arg
+            assert ours[a.arg].default == ast.literal_eval(d), a.arg
+    net = network_tcnn.NeRFNetwork(encoding="HashGrid", desired_resolution=32768, log2_hashmap_size=19,
+                                   n_features_per_level=2, num_layers=2, hidden_dim=64, geo_feat_dim=15, bound=1,
+                                   density_scale=1, min_near=0.2, min_near_lidar=0.0108, density_thresh=10, bg_radius=-1)
+    assert tuple(net.encoder.embeddings.shape) == (6837544, 2)          # SURVEY.md 8a row a5
+    assert net.sigma_net.weights.numel() == 7168 and net.lidar_color_net.weights.numel() == 11264
+    assert net.out_lidar_color_dim == 2 and len(net.get_params(1e-2)) == 6
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k in ("lidarnerf.nerf.network_tcnn",)}
+    try:
+        sys.modules.pop("lidarnerf.nerf.network_tcnn", None)
+        compat.install(patch_lidarnerf=False)
+        assert sys.modules["lidarnerf.nerf.network_tcnn"].NeRFNetwork is network_tcnn.NeRFNetwork
+        assert "tinycudann" not in sys.modules
+    finally:
+        sys.modules.pop("lidarnerf.nerf.network_tcnn", None)
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
