@@ -10,6 +10,7 @@ the resulting small fixtures are committed and pin the CPU oracle / host logic:
   ref_py_run.npz         lidarnerf/nerf/renderer.py:99-298 NeRFRenderer.run (LiDAR mode, perturb=False, eval-mode
                          deterministic PDF up-sampling) with an analytic density/colour field
   ref_py_sample_pdf.npz  lidarnerf/nerf/renderer.py:10-46 sample_pdf(det=True)
+  ref_py_convert.npz     lidarnerf/convert.py:99-160,194-235 lidar_to_pano_with_intensities / pano_to_lidar_with_intensities
 
 Usage: python tests/golden/make_golden_cpu.py
 """
@@ -39,6 +40,32 @@ def save(name, **arrays):
     np.savez_compressed(os.path.join(OUT, name), **{k: np.asarray(v) for k, v in arrays.items()})
     print("wrote", name, {k: np.asarray(v).shape for k, v in arrays.items()})
 
+
+# ---- range image <-> point cloud (lidarnerf/convert.py:99-160,194-235) ---------------------------------------
+def make_convert():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("ref_convert", os.path.join(REF, "lidarnerf", "convert.py"))
+    conv = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(conv)
+    r = np.random.default_rng(5)
+    H, W, K = 32, 256, (2.0, 26.9)
+    n = 6000
+    # points on a few shells + noise, some beyond max_depth, some outside the vertical field of view
+    d = r.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[:, 2] = d[:, 2] * 0.35 - 0.15
+    d /= np.linalg.norm(d, axis=1, keepdims=True)
+    rad = r.choice([5.0, 12.0, 30.0, 70.0, 95.0], size=n) * r.uniform(0.9, 1.1, size=n)
+    pts = np.concatenate([d * rad[:, None], r.uniform(0, 1, size=(n, 1))], axis=1).astype(np.float32)
+    pano, inten = conv.lidar_to_pano_with_intensities(pts, H, W, K, max_depth=80)
+    back = conv.pano_to_lidar_with_intensities(pano.astype(np.float32), inten.astype(np.float32), K)
+    save("ref_py_convert.npz", points=pts, H=H, W=W, K=np.array(K, np.float32), pano=pano, intensities=inten,
+         back=back, numpy_version=np.__version__)
+
+
+make_convert()
+if sys.argv[1:] == ["convert"]:      # `python tests/golden/make_golden_cpu.py convert`: only this fixture
+    sys.exit(0)
 
 # ---- FreqEncoder -------------------------------------------------------------------------------------------
 from lidarnerf.encoding import FreqEncoder  # noqa: E402
@@ -128,29 +155,3 @@ with torch.no_grad():
 save("ref_py_run.npz", rays_o=orig, rays_d=dirs, num_steps=48, upsample_steps=16, min_near_lidar=0.01,
      depth=out["depth_lidar"][0].numpy(), image=out["image_lidar"][0].numpy(),
      weights_sum=out["weights_sum_lidar"].numpy())
-
-# ---- range image <-> point cloud (lidarnerf/convert.py:99-160,194-235) ---------------------------------------
-# (appended in round 1: `python tests/golden/make_golden_cpu.py convert` regenerates only this fixture)
-def make_convert():
-    import importlib.util
-    spec = importlib.util.spec_from_file_location("ref_convert", os.path.join(REF, "lidarnerf", "convert.py"))
-    conv = importlib.util.module_from_spec(spec)
-    spec.loader.exec_module(conv)
-    r = np.random.default_rng(5)
-    H, W, K = 32, 256, (2.0, 26.9)
-    n = 6000
-    # points on a few shells + noise, some beyond max_depth, some outside the vertical field of view
-    d = r.normal(size=(n, 3))
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    d[:, 2] = d[:, 2] * 0.35 - 0.15
-    d /= np.linalg.norm(d, axis=1, keepdims=True)
-    rad = r.choice([5.0, 12.0, 30.0, 70.0, 95.0], size=n) * r.uniform(0.9, 1.1, size=n)
-    pts = np.concatenate([d * rad[:, None], r.uniform(0, 1, size=(n, 1))], axis=1).astype(np.float32)
-    pano, inten = conv.lidar_to_pano_with_intensities(pts, H, W, K, max_depth=80)
-    back = conv.pano_to_lidar_with_intensities(pano.astype(np.float32), inten.astype(np.float32), K)
-    save("ref_py_convert.npz", points=pts, H=H, W=W, K=np.array(K, np.float32), pano=pano, intensities=inten,
-         back=back, numpy_version=np.__version__)
-
-
-if len(sys.argv) > 1 and sys.argv[1] == "convert":
-    make_convert()
