@@ -104,3 +104,31 @@ def test_header_is_plain_c_and_a_c_client_links_and_runs(tmp_path):
     r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "sm_100a" in r.stdout and "invalid argument" in r.stdout
+
+
+def test_engine_and_evaluation_entry_points_reject_null_buffers(L):
+    """Every entry point added for the fused step / the evaluation-side callers validates before it launches."""
+    z, u, f, i, s = C.c_void_p(0), C.c_uint32, C.c_float, C.c_int, C.c_size_t
+    lib = L.lib
+    assert lib.lnb_lidar_composite_step(z, z, z, z, z, z, z, f(0), u(1024), u(1), u(128), z, u(128), u(4), f(1e-4), f(1), f(1),
+                                        f(1), f(1), z, z, z, z, z, z, z, z, z, z) == -1
+    assert lib.lnb_field_forward(z, z, z, z, z, u(128), u(32), u(2), u(96), u(2), u(12), u(64), f(1), z, z, z, z, z, z, z) == -1
+    assert lib.lnb_field_head_backward_rows(z, z, z, z, z, z, z, z, u(128), u(96), u(2), u(12), u(64), f(1), z, z, z, z, z) == -1
+    assert lib.lnb_ffmlp_backward_accumulate_rows(z, z, z, z, u(128), u(32), u(16), u(64), u(2), u(0), u(6), i(1), z, z, z, z,
+                                                  z) == -1
+    assert lib.lnb_grid_encode_backward_rows(z, z, z, z, z, u(128), u(3), u(2), u(16), f(1), u(16), u(0), i(0), u(0), i(1),
+                                             f(1), i(1), z, z, z) == -1
+    assert lib.lnb_grad_total_variation(z, z, z, z, f(1e-7), u(8), u(3), u(2), u(16), f(1), u(16), u(0), i(0), i(0), z) == -1
+    assert lib.lnb_adam_step_dev(z, z, z, z, z, s(16), f(0.9), f(0.99), f(1e-15), z, i(0), z) == -1
+    assert lib.lnb_adam_set_hyper(z, f(1e-2), f(0.1), f(0.01), f(1), i(1), z) == -1
+    assert lib.lnb_dp_adam_exchange(z, z, u(2), z, z, z, s(0), s(16), f(1e-2), f(0.9), f(0.99), f(1e-15), f(0.1), f(0.01),
+                                    f(1), z) == -1
+    assert lib.lnb_chamfer_forward(z, z, u(1), u(8), u(8), z, z, z, z, z) == -1
+    assert lib.lnb_chamfer_backward(z, z, z, z, z, z, z, z, u(1), u(8), u(8), z) == -1
+    assert lib.lnb_lidar_to_pano(z, u(4), u(8), u(64), u(1024), f(2), f(26.9), f(80), z, z, z, z) == -1
+    assert lib.lnb_pano_to_lidar(z, z, u(64), u(1024), f(2), f(26.9), z, z, z, z) == -1
+    assert lib.lnb_pano_to_lidar_workspace_bytes(64, 1024) == 4 * (64 + 1)
+    # more peers than the exchange kernel's pointer table holds: unsupported, not a launch
+    arr = (C.c_void_p * 17)(*([1] * 17))
+    assert lib.lnb_dp_adam_exchange(arr, arr, u(17), C.c_void_p(16), C.c_void_p(16), C.c_void_p(16), s(0), s(16), f(1e-2), f(0.9),
+                                    f(0.99), f(1e-15), f(0.1), f(0.01), f(1), z) == -2      # LNB_ERR_UNSUPPORTED
