@@ -349,6 +349,32 @@ int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, 
                       uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
                       float density_scale, void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
                       const int32_t *n_active, lnb_stream_t stream);
+/* ------------------------------------------------------------------------------------------
+ * ONE persistent kernel per ray packet: lnb_grid_encode_forward_ex + lnb_field_forward in a single launch
+ * (north star of this library; replaces gridencoder.cu:95-199 + ffmlp.cu:460-576 x 2 + the torch glue of
+ * network.py:162-237 between them).  One CTA per SM, warp-specialised: 16 gather warps (warp <-> level) write the
+ * fp16 features straight into the shared-memory operand tile of the first MLP layer while the tensor core (one MMA
+ * warp, tcgen05 + TMEM) and two 128-thread epilogue groups work on earlier tiles.  The MLP weights arrive through the
+ * TMA engine (cp.async.bulk on an mbarrier) from a pre-laid-out image: call lnb_field_pack_weights once per parameter
+ * update.  Results are bit-identical to the two-kernel path; `enc` is still written (the backward pass reads it).
+ * Supported: C = 2 fp16 hash/tiled grids with L*C in {16,32,48,64}, D = 3, linear interpolation, align_corners = 0;
+ * MLP shapes as lnb_field_supported.  lnb_field_fused_weight_bytes returns 0 for unsupported shapes.
+ * ---------------------------------------------------------------------------------------- */
+size_t lnb_field_fused_weight_bytes(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                                    uint32_t degree, uint32_t hidden);
+/* w_sigma / w_head: flat fp16 weights (ffmlp.cu:861-864 layout) -> image [lnb_field_fused_weight_bytes], which must
+ * have been zero-filled once when it was allocated */
+int lnb_field_pack_weights(const void *w_sigma, const void *w_head, uint32_t enc_dim, uint32_t sigma_layers,
+                           uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden, void *image,
+                           lnb_stream_t stream);
+/* xyzs [M,3] fp32 in [-in_bound, in_bound] (in_bound = 0: already in [0,1]); table/offsets/L/C/S/H as
+ * lnb_grid_encode_forward; outputs as lnb_grid_encode_forward_ex (enc, [M, L*C] layout) + lnb_field_forward */
+int lnb_field_fused_forward(const float *xyzs, const void *table, const int32_t *offsets, uint32_t L, uint32_t C, float S,
+                            uint32_t H, float in_bound, const void *weight_image, const int32_t *ray_ids,
+                            const float *ray_bias, uint32_t M, uint32_t sigma_layers, uint32_t head_in_pad,
+                            uint32_t head_layers, uint32_t degree, uint32_t hidden, float density_scale, void *enc,
+                            void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                            const int32_t *n_active, lnb_stream_t stream);
 /* LiDAR-head backward = lnb_field_head_out_grad + lnb_ffmlp_backward_accumulate(head) + lnb_field_sigma_out_grad:
  * g_rgb/rgb [M,2], g_sigma [M] -> g_sig_out [M,16] fp16 (gradient w.r.t. the density MLP's output row) and
  * grad_w_head_f32 (+=, flat fp32, head weight layout). */

@@ -20,6 +20,8 @@ lib.lnb_strerror.restype = C.c_char_p
 lib.lnb_strerror.argtypes = [C.c_int]
 lib.lnb_arch.restype = C.c_char_p
 lib.lnb_launch_count.restype = C.c_uint64
+lib.lnb_field_fused_weight_bytes.restype = C.c_size_t
+lib.lnb_field_fused_weight_bytes.argtypes = [C.c_uint32] * 6
 lib.lnb_ffmlp_backward_workspace_bytes.restype = C.c_size_t
 lib.lnb_ffmlp_backward_workspace_bytes.argtypes = [C.c_uint32] * 4
 for _n in ("lnb_lidar_to_pano_workspace_bytes", "lnb_pano_to_lidar_workspace_bytes"):
@@ -48,6 +50,7 @@ SYMBOLS = [
     "lnb_chamfer_forward", "lnb_chamfer_backward", "lnb_lidar_to_pano_workspace_bytes", "lnb_lidar_to_pano",
     "lnb_pano_to_lidar_workspace_bytes", "lnb_pano_to_lidar",
     "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
+    "lnb_field_fused_weight_bytes", "lnb_field_pack_weights", "lnb_field_fused_forward",
 ]
 
 

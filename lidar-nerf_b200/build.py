@@ -17,7 +17,7 @@ CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIB_DIR, "liblnb200.so")
-UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "field", "optim", "fused", "pointcloud"]
+UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "field", "field_fused", "optim", "fused", "pointcloud"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

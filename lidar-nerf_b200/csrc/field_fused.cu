@@ -1,0 +1,532 @@
+// One persistent kernel per ray packet: hash-grid gather -> density MLP -> LiDAR head (forward).
+//
+// What the two-kernel forward (k_grid_fwd -> enc [M,32] in HBM -> k_field_fwd) did in sequence - an L1/L2-gather-bound
+// kernel followed by a latency-bound tensor-core kernel, each owning the whole SM while the other's units idle - runs
+// here concurrently inside ONE CTA per SM, warp-specialised:
+//
+//   warps  0..15  GATHER     warp <-> level (32 neighbouring samples per gather instruction, all 8 corner loads of a
+//                            sample in flight), results written as fp16 pairs STRAIGHT INTO the swizzled shared-memory
+//                            operand tile of the first MLP layer (a ring of kStages tiles, full/empty mbarriers);
+//   warps 16..23  EPILOGUE   two groups of 128 threads (thread = tile row), one 128-row tile in flight each:
+//                            tcgen05.ld accumulator row -> (+per-ray bias) -> ReLU -> fp16 -> operand tile of the next
+//                            layer (+ the saved activation row to HBM straight from registers); sigma = exp(h0), geo
+//                            features -> head operand; sigmoid -> (ray-drop, intensity);
+//   warp   24     MMA        one elected lane issues every tcgen05.mma of the CTA (M128 x N64/N16 x K16, fp32
+//                            accumulators in tensor memory, 128 columns per group), polling the groups' mbarriers.
+//
+// MLP weights are staged ONCE per CTA by the TMA engine: `lnb_field_pack_weights` lays the six weight tiles out in global
+// memory as the exact shared-memory image (128-byte rows, 16-byte chunks xor-swizzled) and the kernel pulls that image
+// with cp.async.bulk (SASS UBLKCP) onto an mbarrier - no per-thread LDGSTS, no register staging.
+//
+// Numerics are those of k_grid_fwd + k_field_fwd (same helpers, same rounding points): tests compare the two paths
+// bit-for-bit on the saved activations.
+//
+// Reference behaviour: gridencoder.cu:95-199 (gather), ffmlp.cu:460-576 (MLP), network.py:162-237 (wiring).
+#include "common.cuh"
+#include "grid_common.cuh"
+#include "mlp_tiles.cuh"
+
+namespace lnb {
+namespace {
+
+constexpr uint32_t kGatherWarps = 16;
+constexpr uint32_t kGatherThreads = kGatherWarps * 32;
+constexpr uint32_t kGroups = 2;                        // tiles in flight in the MLP part (epilogue groups)
+constexpr uint32_t kGroupThreads = 128;
+constexpr uint32_t kEpiWarp0 = kGatherWarps;           // first epilogue warp (multiple of 4: TMEM lane quadrants)
+constexpr uint32_t kMmaWarpIdx = kEpiWarp0 + kGroups * 4;
+constexpr uint32_t kFusedThreads = (kMmaWarpIdx + 1) * 32;      // 800
+constexpr uint32_t kStages = 3;                        // operand tiles between the gather and the first MLP layer
+constexpr uint32_t kTmemColsPerGroup = 128;            // [0,64) hidden accumulator, [64,80) output accumulator
+
+struct FusedShape {
+    uint32_t enc_dim;        // L * C (multiple of 16, <= 64)
+    uint32_t n_hid_s, n_hid_h;
+    uint32_t head_in;        // padded head input width (row length of W_in of the head)
+    uint32_t nfreq, geo_tile, geo_off, ks_geo;
+};
+
+__host__ __device__ inline uint32_t weight_image_bytes(const FusedShape &fs) {
+    return kWTileBytes * (1 + fs.n_hid_s) + 2048 + kWTileBytes * (1 + fs.n_hid_h) + 2048;
+}
+
+struct FusedArgs {
+    const float *xyz;
+    const __half *table;
+    const int32_t *offsets;
+    uint32_t L;
+    float S;
+    uint32_t H;
+    float2 norm;
+    const uint8_t *wimg;
+    const int32_t *ray_ids;
+    const float *ray_bias;
+    uint32_t B;
+    const int32_t *n_active;
+    FusedShape fs;
+    float density_scale;
+    __half *enc, *fb_s, *sig_out, *fb_h;
+    float *sigma, *rgb;
+};
+
+__device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
+    asm volatile("st.shared.b32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ void sts16h(uint32_t addr, unsigned short v) {
+    asm volatile("st.shared.b16 [%0], %1;" ::"r"(addr), "h"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t elem_addr(uint32_t tile, uint32_t row, uint32_t col) {
+    return tile_chunk_addr(tile, row, col >> 3) + (col & 7u) * 2u;
+}
+__device__ __forceinline__ void named_bar(uint32_t id, uint32_t n) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
+}
+// non-blocking phase test, warp-uniform result (the MMA warp stays converged)
+__device__ __forceinline__ bool mbar_test_warp(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return __all_sync(0xffffffffu, done) != 0;
+}
+
+// -----------------------------------------------------------------------------------------------------
+// weight image: [Ws_in | Ws_hid x n | Ws_out (2 KB) | Wh_geo | Wh_hid x n | Wh_out (2 KB)], every tile in the
+// one operand layout of tcgen05.cuh (tile_chunk_addr).  Chunks that hold no weight stay zero (the image is cleared
+// when it is allocated and only valid chunks are ever written).
+// -----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+k_pack_field_weights(const __half *__restrict__ Ws, const __half *__restrict__ Wh, FusedShape fs, uint8_t *__restrict__ img) {
+    auto put = [&](uint32_t tile_off, const __half *src, uint32_t rows, uint32_t cols, uint32_t ld) {
+        const uint32_t cpr = (cols + 7) / 8;
+        for (uint32_t q = blockIdx.x * blockDim.x + threadIdx.x; q < rows * cpr; q += gridDim.x * blockDim.x) {
+            const uint32_t r = q / cpr, c = q - r * cpr;
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + (size_t)r * ld + c * 8);
+            *reinterpret_cast<uint4 *>(img + tile_chunk_addr(tile_off, r, c)) = v;
+        }
+    };
+    uint32_t off = 0;
+    const uint32_t ws_in_elems = kHid * fs.enc_dim, wh_in_elems = kHid * fs.head_in;
+    put(off, Ws, kHid, fs.enc_dim, fs.enc_dim);
+    off += kWTileBytes;
+    for (uint32_t l = 0; l < fs.n_hid_s; ++l, off += kWTileBytes) put(off, Ws + ws_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid);
+    put(off, Ws + ws_in_elems + (size_t)fs.n_hid_s * kHid * kHid, kOut, kHid, kHid);
+    off += 2048;
+    // head: only the 64-column tile of W_in that holds the geo columns (the direction columns act through ray_bias)
+    put(off, Wh + fs.geo_tile * 64, kHid, min(64u, fs.head_in - fs.geo_tile * 64), fs.head_in);
+    off += kWTileBytes;
+    for (uint32_t l = 0; l < fs.n_hid_h; ++l, off += kWTileBytes) put(off, Wh + wh_in_elems + (size_t)l * kHid * kHid, kHid, kHid, kHid);
+    put(off, Wh + wh_in_elems + (size_t)fs.n_hid_h * kHid * kHid, kOut, kHid, kHid);
+}
+
+// this thread's accumulator row (64 fp32 columns) -> (+bias) -> ReLU -> fp16: eight 16-byte chunks
+__device__ __forceinline__ void row_relu_pack(uint32_t d_row, const float4 *__restrict__ bias, uint4 (&pk)[8]) {
+    uint32_t v0[32], v1[32];
+    tmem_ld32(d_row, v0);
+    tmem_ld32(d_row + 32, v1);
+    tmem_ld_wait();
+#pragma unroll
+    for (uint32_t c = 0; c < 8; ++c) {
+        float f[8];
+#pragma unroll
+        for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(c < 4 ? v0[c * 8 + e] : v1[(c - 4) * 8 + e]);
+        if (bias) {
+            const float4 b0 = __ldg(bias + c * 2), b1 = __ldg(bias + c * 2 + 1);
+            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+        }
+        pk[c].x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
+        pk[c].y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
+        pk[c].z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
+        pk[c].w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
+    }
+}
+
+__global__ void __launch_bounds__(kFusedThreads, 1)
+k_field_fused_fwd(const FusedArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    const FusedShape fs = a.fs;
+    const uint32_t sbase = (smem_u32(smem_raw) + 1023u) & ~1023u;
+    // weight image (same order as k_pack_field_weights)
+    const uint32_t s_ws_in = sbase;
+    const uint32_t s_ws_hid = s_ws_in + kWTileBytes;
+    const uint32_t s_ws_out = s_ws_hid + fs.n_hid_s * kWTileBytes;
+    const uint32_t s_wh_geo = s_ws_out + 2048;
+    const uint32_t s_wh_hid = s_wh_geo + kWTileBytes;
+    const uint32_t s_wh_out = s_wh_hid + fs.n_hid_h * kWTileBytes;
+    const uint32_t wbytes = weight_image_bytes(fs);
+    const uint32_t s_x0 = sbase + wbytes;                          // kStages operand tiles written by the gather
+    const uint32_t s_h0 = s_x0 + kStages * kTileBytes;             // one activation operand tile per group
+    const uint32_t s_in0 = s_h0 + kGroups * kTileBytes;            // 2 x [128][3] coordinates in [0,1]
+    const uint32_t s_bar = s_in0 + 2 * kRows * 3 * 4;
+    const uint32_t bar_xfull = s_bar, bar_xempty = bar_xfull + 8 * kStages, bar_ready = bar_xempty + 8 * kStages;
+    const uint32_t bar_done = bar_ready + 8 * kGroups, bar_w = bar_done + 8 * kGroups, s_slot = bar_w + 8;
+    float *s_in = reinterpret_cast<float *>(smem_raw + (s_in0 - smem_u32(smem_raw)));
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
+    constexpr uint32_t kTmemCols = kGroups * kTmemColsPerGroup <= 256 ? 256u : 512u;
+
+    if (warp == kMmaWarpIdx) tmem_alloc(s_slot, kTmemCols);
+    if (threadIdx.x == 0) {
+        for (uint32_t s = 0; s < kStages; ++s) {
+            mbar_init(bar_xfull + 8 * s, kGatherWarps);
+            mbar_init(bar_xempty + 8 * s, 1 + kGroupThreads);
+        }
+        for (uint32_t g = 0; g < kGroups; ++g) {
+            mbar_init(bar_ready + 8 * g, kGroupThreads);
+            mbar_init(bar_done + 8 * g, 1);
+        }
+        mbar_init(bar_w, 1);
+        mbar_init_fence();
+        // the TMA engine pulls the pre-laid-out weight image: one transaction count, <= 16 KB per bulk copy
+        mbar_expect_tx(bar_w, wbytes);
+        for (uint32_t o = 0; o < wbytes; o += 16384u)
+            bulk_g2s(sbase + o, a.wimg + o, min(16384u, wbytes - o), bar_w);
+    }
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+    const uint32_t tmem = lds32(s_slot);
+
+    const uint32_t n_tiles = active_rows(a.B, a.n_active) / kRows;
+    const uint32_t n_my = blockIdx.x < n_tiles ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    const uint32_t n_steps = fs.n_hid_s + 2 + fs.n_hid_h + 2;
+    const uint32_t ks_in = fs.enc_dim / 16;
+
+    if (warp < kGatherWarps) {
+        // ======================= GATHER: warp <-> level =======================
+        // register budget: the 16 gather warps give registers back, the 8 epilogue warps (a 64-column accumulator row
+        // per thread) take them (setmaxnreg works per warpgroup = 4 consecutive warps).  Pool arithmetic: the CTA is
+        // launched with 72 registers x 800 threads; 512 gather threads release 16 each = 8192 = 256 epilogue threads x 32
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        const uint32_t tid = threadIdx.x;
+        constexpr uint32_t D = 3, C = 2;
+        // level-uniform quantities, once per kernel (the warp keeps its levels for every tile)
+        const uint32_t level0 = warp;
+        LevelGeo g0 = {};
+        LevelIndex<D> li0 = {};
+        if (level0 < a.L) {
+            g0 = level_geo(a.offsets, level0, a.S, a.H);
+            li0 = level_index<D>(g0, 0u, false);
+        }
+        auto stage_coords = [&](uint32_t k, uint32_t buf) {
+            if (tid < kRows * 3) {
+                const size_t tile = blockIdx.x + (size_t)k * gridDim.x;
+                float x = __ldg(a.xyz + tile * kRows * 3 + tid);
+                if (a.norm.x != 0.f) x = (x + a.norm.x) * a.norm.y;
+                s_in[buf * kRows * 3 + tid] = x;
+            }
+        };
+        if (n_my > 0) stage_coords(0, 0);
+        for (uint32_t k = 0; k < n_my; ++k) {
+            const uint32_t stage = k % kStages, use = k / kStages, buf = k & 1u;
+            named_bar(1, kGatherThreads);                   // s_in[buf] complete; everybody is done with s_in[buf ^ 1]
+            if (k + 1 < n_my) stage_coords(k + 1, buf ^ 1u);
+            if (use > 0) mbar_wait(bar_xempty + 8 * stage, (use - 1) & 1u);
+            const uint32_t s_x = s_x0 + stage * kTileBytes;
+            const float *in = s_in + buf * kRows * 3;
+            for (uint32_t level = level0; level < a.L; level += kGatherWarps) {
+                LevelGeo g = g0;
+                LevelIndex<D> li = li0;
+                if (level != level0) {
+                    g = level_geo(a.offsets, level, a.S, a.H);
+                    li = level_index<D>(g, 0u, false);
+                }
+                const __half *__restrict__ tab = a.table + (size_t)g.table_offset * C;
+#pragma unroll
+                for (uint32_t grp = 0; grp < kRows / 32; ++grp) {
+                    const uint32_t sl = grp * 32 + lane;
+                    float v[D];
+                    bool inside = true;
+#pragma unroll
+                    for (uint32_t d = 0; d < D; ++d) {
+                        v[d] = in[sl * D + d];
+                        if (v[d] < 0 || v[d] > 1) inside = false;
+                    }
+                    const Cell<D> cell = locate_unit<D>(v, inside, g, false, 0u);
+                    __half res[C];
+                    res[0] = res[1] = __float2half_rn(0.f);
+                    if (cell.inside) {
+                        if (li.generic) interp_corners<__half, D, C, true>(cell, g, li, 0u, false, tab, res);
+                        else interp_corners<__half, D, C, false>(cell, g, li, 0u, false, tab, res);
+                    }
+                    sts32(elem_addr(s_x, sl, level * C), (uint32_t)__half_as_ushort(res[0]) | ((uint32_t)__half_as_ushort(res[1]) << 16));
+                }
+            }
+            fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_xfull + 8 * stage);
+        }
+    } else if (warp < kMmaWarpIdx) {
+        // ======================= EPILOGUE groups: thread = tile row =======================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        const uint32_t g = (warp - kEpiWarp0) >> 2;
+        const uint32_t row = (warp & 3u) * 32u + lane;     // = TMEM lane (warp % 4 selects the 32-lane quadrant)
+        const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
+        const uint32_t d_hid = tmem + g * kTmemColsPerGroup + lane_sel;
+        const uint32_t d_out = d_hid + 64;
+        const uint32_t s_h = s_h0 + g * kTileBytes;
+        const uint32_t ready = bar_ready + 8 * g, done = bar_done + 8 * g;
+        uint32_t par = 0;
+        if (g < n_my) mbar_arrive(ready);                   // tensor memory of this group is free: first tile may start
+        for (uint32_t k = g; k < n_my; k += kGroups) {
+            const uint32_t stage = k % kStages, use = k / kStages;
+            const size_t row0 = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * kRows;
+            const size_t r = row0 + row;
+            const uint32_t rid = (uint32_t)__ldg(a.ray_ids + r);
+            // while the first layer's MMA runs: this row of the gathered features -> enc (the backward pass needs it),
+            // then release the operand tile to the gather warps
+            mbar_wait(bar_xfull + 8 * stage, use & 1u);
+            {
+                const uint32_t s_x = s_x0 + stage * kTileBytes;
+                uint4 *dst = reinterpret_cast<uint4 *>(a.enc + r * fs.enc_dim);
+                for (uint32_t c = 0; c < fs.enc_dim / 8; ++c) dst[c] = lds128(tile_chunk_addr(s_x, row, c));
+            }
+            mbar_arrive(bar_xempty + 8 * stage);
+            // this row's 256 B of the per-ray head bias, needed four layers from now: pull the lines into L1
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid * kHid));
+            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid * kHid + 32));
+
+            // ---------------- density MLP ----------------
+            for (uint32_t layer = 0; layer <= fs.n_hid_s; ++layer) {
+                mbar_wait(done, par);
+                par ^= 1;
+                fence_after_sync();
+                uint4 pk[8];
+                row_relu_pack(d_hid, nullptr, pk);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
+                fence_proxy_async();
+                fence_before_sync();
+                mbar_arrive(ready);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.fb_s + ((size_t)layer * a.B + r) * kHid);   // while the tensor core works
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) dst[c] = pk[c];
+            }
+            // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand tile
+            mbar_wait(done, par);
+            par ^= 1;
+            fence_after_sync();
+            {
+                uint32_t v[16];
+                tmem_ld16(d_out, v);
+                tmem_ld_wait();
+                __half hv[16];
+#pragma unroll
+                for (uint32_t j = 0; j < 16; ++j) hv[j] = __float2half_rn(__uint_as_float(v[j]));
+                const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.sig_out + r * kOut);
+                dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+                a.sigma[r] = __expf(__half2float(hv[0])) * a.density_scale;    // activation.py:6-20 (forward)
+                for (uint32_t c = 0; c < 2 * fs.ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
+#pragma unroll
+                for (uint32_t j = 1; j < 16; ++j) sts16h(elem_addr(s_h, row, fs.geo_off + j - 1), __half_as_ushort(hv[j]));
+            }
+            fence_proxy_async();
+            fence_before_sync();
+            mbar_arrive(ready);
+
+            // ---------------- LiDAR head ----------------
+            const float4 *bias = reinterpret_cast<const float4 *>(a.ray_bias + (size_t)rid * kHid);
+            for (uint32_t layer = 0; layer <= fs.n_hid_h; ++layer) {
+                mbar_wait(done, par);
+                par ^= 1;
+                fence_after_sync();
+                uint4 pk[8];
+                row_relu_pack(d_hid, layer == 0 ? bias : nullptr, pk);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
+                fence_proxy_async();
+                fence_before_sync();
+                mbar_arrive(ready);
+                uint4 *dst = reinterpret_cast<uint4 *>(a.fb_h + ((size_t)layer * a.B + r) * kHid);
+#pragma unroll
+                for (uint32_t c = 0; c < 8; ++c) dst[c] = pk[c];
+            }
+            // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
+            mbar_wait(done, par);
+            par ^= 1;
+            fence_after_sync();
+            {
+                uint32_t v[16];
+                tmem_ld16(d_out, v);
+                tmem_ld_wait();
+                const float x0 = __half2float(__float2half_rn(__uint_as_float(v[0])));
+                const float x1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
+                reinterpret_cast<float2 *>(a.rgb)[r] = make_float2(1.f / (1.f + __expf(-x0)), 1.f / (1.f + __expf(-x1)));
+            }
+            fence_before_sync();                            // this tile's TMEM reads are ordered before the next tile's MMAs
+            if (k + kGroups < n_my) mbar_arrive(ready);     // tensor memory drained: the group's next tile may start
+        }
+    } else {
+        // ======================= MMA warp (converged; one elected lane issues) =======================
+        mbar_wait_warp(bar_w, 0);                           // weight image landed (TMA transaction bytes complete)
+        uint32_t kk[kGroups], step[kGroups], par[kGroups];
+        uint32_t left = 0;
+#pragma unroll
+        for (uint32_t g = 0; g < kGroups; ++g) {
+            kk[g] = g, step[g] = 0, par[g] = 0;
+            if (g < n_my) ++left;
+        }
+        uint32_t spins = 0;
+        while (left > 0) {
+            bool progressed = false;
+#pragma unroll
+            for (uint32_t g = 0; g < kGroups; ++g) {
+                if (kk[g] >= n_my) continue;
+                if (!mbar_test_warp(bar_ready + 8 * g, par[g])) continue;
+                const uint32_t stage = kk[g] % kStages, use = kk[g] / kStages;
+                if (step[g] == 0 && !mbar_test_warp(bar_xfull + 8 * stage, use & 1u)) continue;
+                par[g] ^= 1;
+                fence_after_sync();
+                const uint32_t d_hid = tmem + g * kTmemColsPerGroup, d_out = d_hid + 64;
+                const uint32_t s_h = s_h0 + g * kTileBytes;
+                const uint32_t st = step[g];
+                if (st == 0) {
+                    issue_kmajor(d_hid, s_x0 + stage * kTileBytes, s_ws_in, ks_in, kIdescFwdHid, false);
+                } else if (st <= fs.n_hid_s) {
+                    issue_kmajor(d_hid, s_h, s_ws_hid + (st - 1) * kWTileBytes, 4, kIdescFwdHid, false);
+                } else if (st == fs.n_hid_s + 1) {
+                    issue_kmajor(d_out, s_h, s_ws_out, 4, kIdescFwdOut, false);
+                } else if (st == fs.n_hid_s + 2) {
+                    issue_kmajor(d_hid, s_h, s_wh_geo, fs.ks_geo, kIdescFwdHid, false);
+                } else if (st <= fs.n_hid_s + 2 + fs.n_hid_h) {
+                    issue_kmajor(d_hid, s_h, s_wh_hid + (st - fs.n_hid_s - 3) * kWTileBytes, 4, kIdescFwdHid, false);
+                } else {
+                    issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
+                }
+                mma_commit_elect(bar_done + 8 * g);
+                if (st == 0) mma_commit_elect(bar_xempty + 8 * stage);     // the operand tile has been consumed
+                if (++step[g] == n_steps) {
+                    step[g] = 0;
+                    kk[g] += kGroups;
+                    if (kk[g] >= n_my) --left;
+                }
+                progressed = true;
+            }
+            if (progressed) spins = 0;
+            else if (++spins > (1u << 24)) __trap();        // a protocol bug becomes a kernel error, not a hung GPU
+        }
+    }
+
+    fence_before_sync();
+    __syncthreads();
+    if (warp == kMmaWarpIdx) tmem_dealloc(tmem, kTmemCols);
+}
+
+int make_fused_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree,
+                     uint32_t hidden, FusedShape *fs) {
+    if (hidden != kHid) return LNB_ERR_UNSUPPORTED;
+    if (enc_dim == 0 || enc_dim % 16 != 0 || enc_dim > 64) return LNB_ERR_UNSUPPORTED;
+    if (head_in_pad == 0 || head_in_pad % 16 != 0 || head_in_pad > 128) return LNB_ERR_UNSUPPORTED;
+    if (sigma_layers < 2 || head_layers < 2 || sigma_layers > 4 || head_layers > 4) return LNB_ERR_UNSUPPORTED;
+    fs->enc_dim = enc_dim;
+    fs->n_hid_s = sigma_layers - 1;
+    fs->n_hid_h = head_layers - 1;
+    fs->head_in = head_in_pad;
+    fs->nfreq = 3 + 6 * degree;
+    if (fs->nfreq + 15 > head_in_pad) return LNB_ERR_INVALID_ARGUMENT;
+    fs->geo_tile = fs->nfreq / 64;
+    fs->geo_off = fs->nfreq % 64;
+    if (fs->geo_off + 15 > 64) return LNB_ERR_UNSUPPORTED;      // geo columns must sit inside one 64-column tile
+    fs->ks_geo = (fs->geo_off + 15 + 15) / 16;
+    return LNB_OK;
+}
+
+size_t fused_smem_bytes(const FusedShape &fs) {
+    return 1024 + weight_image_bytes(fs) + (size_t)(kStages + kGroups) * kTileBytes + 2 * kRows * 3 * 4 +
+           8 * (2 * kStages + 2 * kGroups + 1) + 16;
+}
+
+int sm_count_fused() {
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        if (n <= 0) n = 148;
+    }
+    return n;
+}
+
+}  // namespace
+}  // namespace lnb
+
+using namespace lnb;
+
+extern "C" {
+
+size_t lnb_field_fused_weight_bytes(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                                    uint32_t degree, uint32_t hidden) {
+    FusedShape fs;
+    if (make_fused_shape(enc_dim, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs) != LNB_OK) return 0;
+    if (fused_smem_bytes(fs) > 226 * 1024) return 0;
+    return weight_image_bytes(fs);
+}
+
+int lnb_field_pack_weights(const void *w_sigma, const void *w_head, uint32_t enc_dim, uint32_t sigma_layers,
+                           uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden, void *image,
+                           lnb_stream_t stream) {
+    if (!w_sigma || !w_head || !image) return LNB_ERR_INVALID_ARGUMENT;
+    FusedShape fs;
+    int rc = make_fused_shape(enc_dim, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
+    if (rc != LNB_OK) return rc;
+    k_pack_field_weights<<<8, 256, 0, as_stream(stream)>>>(static_cast<const __half *>(w_sigma), static_cast<const __half *>(w_head),
+                                                          fs, static_cast<uint8_t *>(image));
+    count_launch();
+    return launch_status();
+}
+
+int lnb_field_fused_forward(const float *xyzs, const void *table, const int32_t *offsets, uint32_t L, uint32_t C, float S,
+                            uint32_t H, float in_bound, const void *weight_image, const int32_t *ray_ids,
+                            const float *ray_bias, uint32_t M, uint32_t sigma_layers, uint32_t head_in_pad,
+                            uint32_t head_layers, uint32_t degree, uint32_t hidden, float density_scale, void *enc,
+                            void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                            const int32_t *n_active, lnb_stream_t stream) {
+    if (!xyzs || !table || !offsets || !weight_image || !ray_ids || !ray_bias || !enc || !fb_sigma || !sig_out || !sigma ||
+        !fb_head || !rgb)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (M % kRows != 0 || L == 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (C != 2) return LNB_ERR_UNSUPPORTED;
+    FusedShape fs;
+    int rc = make_fused_shape(L * C, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
+    if (rc != LNB_OK) return rc;
+    const size_t smem = fused_smem_bytes(fs);
+    if (smem > 226 * 1024) return LNB_ERR_UNSUPPORTED;
+    if (M == 0) return LNB_OK;
+    cudaError_t e = cudaFuncSetAttribute(k_field_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) { cudaGetLastError(); return (int)e; }
+    FusedArgs a = {};
+    a.xyz = xyzs;
+    a.table = static_cast<const __half *>(table);
+    a.offsets = offsets;
+    a.L = L;
+    a.S = S;
+    a.H = H;
+    a.norm = in_bound > 0.f ? make_float2(in_bound, 1.0f / (2.0f * in_bound)) : make_float2(0.f, 0.f);
+    a.wimg = static_cast<const uint8_t *>(weight_image);
+    a.ray_ids = ray_ids;
+    a.ray_bias = ray_bias;
+    a.B = M;
+    a.n_active = n_active;
+    a.fs = fs;
+    a.density_scale = density_scale;
+    a.enc = static_cast<__half *>(enc);
+    a.fb_s = static_cast<__half *>(fb_sigma);
+    a.sig_out = static_cast<__half *>(sig_out);
+    a.fb_h = static_cast<__half *>(fb_head);
+    a.sigma = sigma;
+    a.rgb = rgb;
+    const uint32_t tiles = M / kRows;
+    const uint32_t cap = (uint32_t)sm_count_fused();
+    k_field_fused_fwd<<<tiles < cap ? tiles : cap, kFusedThreads, smem, as_stream(stream)>>>(a);
+    count_launch();
+    return launch_status();
+}
+
+}  // extern "C"

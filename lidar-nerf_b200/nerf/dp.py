@@ -51,8 +51,10 @@ class ShardedExchange:
     per rank instead of 8 B/param for a gradient all-reduce, and the optimiser touches 1/world of the Adam state.
     """
 
-    def __init__(self, n, align=8):
-        self.world, self.rank = world_size(), rank()
+    def __init__(self, n, align=8, local_only=False):
+        """local_only: a one-rank layout regardless of the process group (parameters owned and synchronised by someone
+        else, e.g. a DistributedDataParallel wrapper around the nn.Module path)."""
+        self.world, self.rank = (1, 0) if local_only else (world_size(), rank())
         unit = self.world * align
         self.n = n
         self.n_padded = (n + unit - 1) // unit * unit

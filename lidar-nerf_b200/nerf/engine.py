@@ -21,7 +21,6 @@ The step, in launch order:
 """
 import ctypes as C
 import math
-from dataclasses import dataclass
 
 import numpy as np
 import torch
@@ -30,63 +29,7 @@ from ..backend import (_raymarching as rm, _ffmlp as ff, adam_step)
 from .._lib import lib, check, u32, f32, i32, vp, sz, launch_count
 from ..gridencoder import level_offsets
 from . import dp
-
-
-@dataclass
-class FieldConfig:
-    # scene / march (main_lidarnerf.py defaults; configs/kitti360_1908.txt)
-    bound: float = 1.0
-    grid_size: int = 128                 # renderer.py:75
-    min_near_lidar: float = 0.010784853507573345   # = opt.scale (main_lidarnerf.py:286-287)
-    far_factor: float = 81.0             # renderer.py:134-138
-    dt_gamma: float = 0.0
-    max_steps: int = 1024
-    T_thresh: float = 1e-4
-    density_scale: float = 1.0
-    density_thresh: float = 10.0         # main_lidarnerf.py:210-215
-    # hash grid (configs/kitti360_1908.txt:7, main_lidarnerf.py:68-69)
-    num_levels: int = 16
-    level_dim: int = 2
-    base_resolution: int = 16
-    desired_resolution: int = 32768
-    log2_hashmap_size: int = 19
-    # MLPs (ffmlp 64x2 each; network.py:45-99 shapes)
-    hidden_dim: int = 64
-    sigma_layers: int = 2                # FFMLP num_layers
-    head_layers: int = 2
-    freq_degree: int = 12                # network.py:83
-    geo_feat_dim: int = 15
-    # loss (configs/kitti360_1908.txt:2-4)
-    alpha_d: float = 1e3
-    alpha_r: float = 1.0
-    alpha_i: float = 10.0
-    # optimiser (main_lidarnerf.py:389-391, lr default 1e-2)
-    lr: float = 1e-2
-    beta1: float = 0.9
-    beta2: float = 0.99
-    eps: float = 1e-15
-    loss_scale: float = 128.0            # static loss scale for the fp16 gradient chain (GradScaler's role)
-    grid_update_interval: int = 16
-    perturb: bool = True                 # jitter the march start (Trainer.train_step passes perturb=True)
-    fused_field: bool = True             # density MLP + LiDAR head as the fused field kernels (csrc/field.cu)
-    fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
-    compact_backward: bool = True        # backward kernels walk only the samples up to each ray's early stop
-    late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam
-    fused_exchange: bool = True          # data parallel: one peer-memory kernel (reduce-scatter + Adam + all-gather) over
-                                         # NVLink via torch symmetric memory; falls back to NCCL when it cannot be set up
-    overlap_exchange: bool = True        # data parallel, graph mode: the exchange overlaps the next step's march
-    pipeline_adam: bool = False          # graph mode, one rank: Adam of step i runs next to the march of step i+1
-                                         # (measured: -6 us/step device time, +CPU launch work; off by default)
-    seed: int = 0
-
-    @property
-    def cascade(self):
-        return 1 + math.ceil(math.log2(self.bound))   # renderer.py:74
-
-    @property
-    def head_in_dim(self):
-        raw = 3 + 6 * self.freq_degree + self.geo_feat_dim        # 75 + 15 = 90
-        return (raw + 15) // 16 * 16                               # padded to 96 for the tensor cores
+from .config import FieldConfig   # noqa: F401  (re-exported: `from ...engine import FieldConfig` keeps working)
 
 
 def _ck(status, what):
@@ -94,8 +37,13 @@ def _ck(status, what):
 
 
 class LidarFieldEngine:
-    def __init__(self, cfg: FieldConfig, n_rays: int, device="cuda:0", sample_budget: int = None):
+    def __init__(self, cfg: FieldConfig, n_rays: int, device="cuda:0", sample_budget: int = None,
+                 external_params: bool = False):
+        """external_params=True: the engine is a WORKSPACE for parameters owned by someone else (the nn.Module path,
+        nerf/fused_render.py): only the fp16 shadow `Ph` exists (filled by `load_params`), no fp32 master / Adam moments /
+        gradient vector (the caller hands a gradient buffer to `set_grad_buffer` before the backward kernels run)."""
         self.cfg = cfg
+        self.external_params = bool(external_params)
         self.dev = torch.device(device)
         self.N = int(n_rays)
         c = cfg
@@ -116,16 +64,21 @@ class LidarFieldEngine:
         self.n_table, self.n_sigma, self.n_head = n_table, n_sigma, n_head
         n = n_table + n_sigma + n_head
         self.n_params = n
-        self.ex = dp.ShardedExchange(n)                 # data-parallel layout of the flat vectors (1 rank: identity)
+        self.ex = dp.ShardedExchange(n, local_only=self.external_params)   # data-parallel layout of the flat vectors
         npad = self.ex.n_padded
-        P = torch.zeros(npad, dtype=torch.float32)
-        P[:n_table].uniform_(-1e-4, 1e-4, generator=gen)                                   # grid.py:202-204
-        bound_w = math.sqrt(3 / c.hidden_dim)                                              # ffmlp.py:242-245
-        P[n_table:n].uniform_(-bound_w, bound_w, generator=gen)
-        self.G = torch.zeros(npad, dtype=torch.float32, device=dev)
-        self.Ph = P.to(dev).to(torch.float16)
         self._peer = None
-        if self.ex.world > 1 and c.fused_exchange:
+        if self.external_params:
+            P = None
+            self.Ph = torch.zeros(npad, dtype=torch.float16, device=dev)
+            self.G = None
+        else:
+            P = torch.zeros(npad, dtype=torch.float32)
+            P[:n_table].uniform_(-1e-4, 1e-4, generator=gen)                                   # grid.py:202-204
+            bound_w = math.sqrt(3 / c.hidden_dim)                                              # ffmlp.py:242-245
+            P[n_table:n].uniform_(-bound_w, bound_w, generator=gen)
+            self.G = torch.zeros(npad, dtype=torch.float32, device=dev)
+            self.Ph = P.to(dev).to(torch.float16)
+        if self.ex.world > 1 and c.fused_exchange and not self.external_params:
             # gradient and fp16 shadow in symmetric (peer-mapped) memory: the exchange becomes ONE kernel that reads every
             # rank's gradient shard and writes every rank's shadow over NVLink (lnb_dp_adam_exchange); NCCL otherwise
             try:
@@ -147,21 +100,23 @@ class LidarFieldEngine:
                 if self.ex.rank == 0:
                     print(f"[lidar-nerf_b200] symmetric memory unavailable ({type(e).__name__}: {e}); NCCL exchange")
                 self._peer = None
-        if self.ex.world > 1:
+        if self.external_params:
+            self.P = self.m = self.v = None
+        elif self.ex.world > 1:
             # fp32 master weights and Adam moments exist only for this rank's shard (1/world of 3 x 54.8 MB)
             self.P = P[self.ex.lo:self.ex.hi].to(dev)
             self.G_shard = torch.zeros(self.ex.shard, dtype=torch.float32, device=dev)
             self.Ph_shard = torch.empty(self.ex.shard, dtype=torch.float16, device=dev)
         else:
             self.P = P.to(dev)
-        self.m = torch.zeros_like(self.P)
-        self.v = torch.zeros_like(self.P)
+        if not self.external_params:
+            self.m = torch.zeros_like(self.P)
+            self.v = torch.zeros_like(self.P)
         self.table_h = self.Ph[:n_table].view(self.n_rows, c.level_dim)
         self.w_sigma_h = self.Ph[n_table:n_table + n_sigma]
         self.w_head_h = self.Ph[n_table + n_sigma:n]
-        self.g_table = self.G[:n_table]
-        self.g_sigma_w = self.G[n_table:n_table + n_sigma]
-        self.g_head_w = self.G[n_table + n_sigma:n]
+        if self.G is not None:
+            self.set_grad_buffer(self.G)
         self.step_count = 0
 
         # ---- occupancy state -------------------------------------------------------
@@ -199,6 +154,11 @@ class LidarFieldEngine:
         self.fused = bool(c.fused_field) and lib.lnb_field_supported(
             u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
             u32(c.hidden_dim)) == 0
+        # gather + MLPs as one persistent kernel: the MLP weights travel as a pre-laid-out shared-memory image (TMA)
+        wbytes = int(lib.lnb_field_fused_weight_bytes(u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim),
+                                                      u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim)))
+        self.fused_gather = bool(c.fused_gather) and self.fused and wbytes > 0 and c.level_dim == 2
+        self.wimage = torch.zeros(max(wbytes, 16), dtype=torch.uint8, device=dev) if self.fused_gather else None
         self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=torch.float16, device=dev)
         self.ray_bias = torch.zeros(N, c.hidden_dim, **f)
 
@@ -215,6 +175,21 @@ class LidarFieldEngine:
         self._graph_b = None
         self.graph_kernels = 0
         self._alloc_samples(sample_budget or N * 64)
+
+    # ------------------------------------------------------------------------------------------------------
+    def set_grad_buffer(self, G):
+        """Flat fp32 gradient vector [hash table | density MLP | LiDAR head] the backward kernels accumulate into."""
+        a, b, n = self.n_table, self.n_table + self.n_sigma, self.n_params
+        self.G = G
+        self.g_table = G[:a]
+        self.g_sigma_w = G[a:b]
+        self.g_head_w = G[b:n]
+
+    def load_params(self, embeddings, w_sigma, w_head):
+        """fp32 (or fp16) parameters owned by the caller -> the fp16 shadow the kernels read (three cast-copies)."""
+        self.table_h.copy_(embeddings.detach().reshape(self.n_rows, self.cfg.level_dim))
+        self.w_sigma_h.copy_(w_sigma.detach().reshape(-1))
+        self.w_head_h.copy_(w_head.detach().reshape(-1))
 
     # ------------------------------------------------------------------------------------------------------
     def _alloc_samples(self, M):
@@ -279,6 +254,12 @@ class LidarFieldEngine:
 
     def _fb_field(self):
         """Encoding, field network, compositing + loss, backward: everything that reads parameters."""
+        self._fwd_field()
+        self._composite_loss()
+        self._bwd_field()
+
+    def _fwd_field(self):
+        """samples -> hash-grid features -> density MLP -> LiDAR head: sigma [M], rgb [M,2] (+ what backward needs)."""
         c, N, M, s = self.cfg, self.N, self.M, self._s()
         p = lambda t: vp(t.data_ptr())   # noqa: E731
         main = torch.cuda.current_stream()
@@ -289,6 +270,11 @@ class LidarFieldEngine:
                 _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
                                             u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
                     "ray_terms")
+                if self.fused_gather:
+                    _ck(lib.lnb_field_pack_weights(p(self.w_sigma_h), p(self.w_head_h), u32(self.enc_dim),
+                                                   u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
+                                                   u32(c.freq_degree), u32(c.hidden_dim), p(self.wimage), self._s()),
+                        "pack_weights")
         # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
         # (the extended march also zeroes the padding rows of the last tile)
@@ -297,6 +283,16 @@ class LidarFieldEngine:
             main.wait_stream(self._side)               # the pipelined Adam (same side stream) must be done before the gather
         compact = bool(c.compact_backward and c.fused_composite and self.fused)
         nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
+        if self.fused_gather:
+            main.wait_stream(self._side)               # join: ray terms + weight image ready
+            _ck(lib.lnb_field_fused_forward(p(self.xyzs), p(self.table_h), p(self.offsets), u32(c.num_levels),
+                                            u32(c.level_dim), f32(self.S), u32(c.base_resolution), f32(c.bound),
+                                            p(self.wimage), p(self.ray_ids), p(self.ray_bias), u32(M),
+                                            u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
+                                            u32(c.freq_degree), u32(c.hidden_dim), f32(c.density_scale), p(self.enc),
+                                            p(self.fb_sigma), p(self.sig_out), p(self.sigma), p(self.fb_head),
+                                            p(self.rgb), na, s), "field_fused_forward")
+            return
         _ck(lib.lnb_grid_encode_forward_ex(p(self.xyzs), p(self.table_h), p(self.offsets), p(self.enc), u32(M), u32(3),
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), na, s),
@@ -319,6 +315,34 @@ class LidarFieldEngine:
                                          u32(c.hidden_dim), u32(c.head_layers), u32(0), u32(6), p(self.fb_head),
                                          p(self.head_out), na, s), "ffmlp_fwd(head)")
             _ck(lib.lnb_field_head_rgb(p(self.head_out), u32(M), p(self.rgb), na, s), "head_rgb")
+
+    def _compact(self):
+        c = self.cfg
+        return bool(c.compact_backward and c.fused_composite and self.fused)
+
+    def composite_forward(self):
+        """sigma, rgb -> per-ray weights_sum / depth (relative to the march start t0) / image (raymarching.cu:578-676)."""
+        c = self.cfg
+        rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, self.M, self.N, c.T_thresh, 2,
+                                           self.ws, self.depth, self.image)
+
+    def composite_backward(self):
+        """per-ray gradients in g_ws / g_depth / g_image -> g_sigma, g_rgb (with the depth gradient the reference drops,
+        raymarching.py:329-330)."""
+        c = self.cfg
+        self.g_sigma.zero_()
+        self.g_rgb.zero_()
+        rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb,
+                                            self.deltas, self.rays, self.ws, self.depth, self.image, self.M, self.N,
+                                            c.T_thresh, 2, self.g_sigma, self.g_rgb)
+
+    def _composite_loss(self):
+        """compositing forward + LiDAR loss + compositing backward: one kernel (fused_composite) or the per-op chain."""
+        c, N, M, s = self.cfg, self.N, self.M, self._s()
+        p = lambda t: vp(t.data_ptr())   # noqa: E731
+        na = p(self.counter)
+        compact = self._compact()
+        nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
         if c.fused_composite:
             _ck(lib.lnb_lidar_composite_step(p(self.sigma), p(self.rgb), p(self.deltas), p(self.rays), p(self.gt),
                                              p(self.nears), p(self.noises), f32(c.dt_gamma), u32(c.max_steps),
@@ -328,17 +352,19 @@ class LidarFieldEngine:
                                              p(self.g_rgb), p(self.loss_acc), p(self.live_idx) if compact else vp(0),
                                              nl if compact else vp(0), s), "lidar_composite_step")
         else:
-            rm.composite_rays_train_forward_ex(self.sigma, self.rgb, self.deltas, self.rays, M, N, c.T_thresh, 2,
-                                               self.ws, self.depth, self.image)
+            self.composite_forward()
             _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N),
                                    f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale), p(self.g_ws),
                                    p(self.g_depth), p(self.g_image), p(self.loss_acc), s), "lidar_loss")
-            # ---- backward ----
-            self.g_sigma.zero_()
-            self.g_rgb.zero_()
-            rm.composite_rays_train_backward_ex(self.g_ws, self.g_depth, self.g_image, self.sigma, self.rgb,
-                                                self.deltas, self.rays, self.ws, self.depth, self.image, M, N,
-                                                c.T_thresh, 2, self.g_sigma, self.g_rgb)
+            self.composite_backward()
+
+    def _bwd_field(self):
+        """g_sigma, g_rgb -> gradient of the LiDAR head, the density MLP and the hash table (accumulated into G)."""
+        c, N, M, s = self.cfg, self.N, self.M, self._s()
+        p = lambda t: vp(t.data_ptr())   # noqa: E731
+        na = p(self.counter)
+        compact = self._compact()
+        nl = vp(self.counter.data_ptr() + 8)
         if c.late_grad_zero:
             # The 55 MB fp32 gradient table is cleared HERE, a few microseconds before the scatter-add, instead of by
             # Adam half a millisecond (and ~1 GB of other traffic) earlier: the zeroed lines are still in the 126 MB L2

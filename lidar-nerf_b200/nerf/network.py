@@ -27,10 +27,11 @@ def _run_stack(layers, h):
 
 
 class NeRFNetwork(NeRFRenderer):
-    def __init__(self, encoding="hashgrid", encoding_dir="frequency", multires=15, desired_resolution=2048,
-                 log2_hashmap_size=19, num_layers=2, hidden_dim=64, geo_feat_dim=15, num_layers_color=3,
-                 hidden_dim_color=64, out_color_dim=3, out_lidar_color_dim=2, bound=1, use_ffmlp=True, level_dim=2,
-                 **kwargs):
+    def __init__(self, encoding="hashgrid", encoding_dir="frequency", multires=15, encoding_bg="hashgrid",
+                 desired_resolution=2048, log2_hashmap_size=19, num_layers=2, hidden_dim=64, geo_feat_dim=15,
+                 num_layers_color=3, hidden_dim_color=64, num_layers_bg=2, hidden_dim_bg=64, out_color_dim=3,
+                 out_lidar_color_dim=2, bound=1, use_ffmlp=True, level_dim=2, **kwargs):
+        # positional order and keyword set of network.py:11-30 (+ use_ffmlp / level_dim, this package's extensions)
         super().__init__(bound, **kwargs)
         self.num_layers, self.hidden_dim, self.geo_feat_dim = num_layers, hidden_dim, geo_feat_dim
         self.num_layers_color, self.hidden_dim_color = num_layers_color, hidden_dim_color
@@ -49,8 +50,10 @@ class NeRFNetwork(NeRFRenderer):
             from ..ffmlp import FFMLP
             pad = lambda n: (n + 15) // 16 * 16   # noqa: E731
             self.pad_in, self.pad_rgb, self.pad_lidar = pad(self.in_dim), pad(raw_rgb), pad(raw_lidar)
-            # FFMLP needs >= 3 matmuls: a num_layers-deep nn.Linear stack maps to max(num_layers - 1, 2) FFMLP layers
-            self.sigma_net = FFMLP(self.pad_in, 1 + geo_feat_dim, hidden_dim, max(num_layers, 2))
+            # An FFMLP with L layers has L + 1 matmuls and needs L >= 2 (ffmlp.py:217): a num_layers-deep nn.Linear stack
+            # (num_layers matmuls) maps to max(num_layers - 1, 2) FFMLP layers - for the default num_layers = 2 that is
+            # one matmul more than the reference's two-Linear density net, the smallest FFMLP there is.
+            self.sigma_net = FFMLP(self.pad_in, 1 + geo_feat_dim, hidden_dim, max(num_layers - 1, 2))
             self.color_net = FFMLP(self.pad_rgb, out_color_dim, hidden_dim_color, max(num_layers_color - 1, 2))
             self.lidar_color_net = FFMLP(self.pad_lidar, out_lidar_color_dim, hidden_dim_color,
                                          max(num_layers_color - 1, 2))
@@ -58,6 +61,15 @@ class NeRFNetwork(NeRFRenderer):
             self.sigma_net = _linear_stack(self.in_dim, hidden_dim, 1 + geo_feat_dim, num_layers)
             self.color_net = _linear_stack(raw_rgb, hidden_dim_color, out_color_dim, num_layers_color)
             self.lidar_color_net = _linear_stack(raw_lidar, hidden_dim_color, out_lidar_color_dim, num_layers_color)
+        if self.bg_radius > 0:
+            # network.py:100-128 builds a 2-D hash grid + MLP for a background sphere; the LiDAR branch never blends a
+            # background (renderer.py:277-290 is skipped for cal_lidar_color) and this package does not provide one
+            raise NotImplementedError("bg_radius > 0 (background model) is not implemented in lidar-nerf_b200; the LiDAR "
+                                      "branch does not use it - pass bg_radius <= 0")
+
+    def fused_unsupported_reason(self):
+        from .fused_render import FusedLidarRender
+        return FusedLidarRender.supported(self)
 
     @staticmethod
     def _pad(h, width):
@@ -70,7 +82,9 @@ class NeRFNetwork(NeRFRenderer):
                 h = self.sigma_net(self._pad(h, self.pad_in))
         else:
             h = _run_stack(self.sigma_net, h)
-        return {"sigma": trunc_exp(h[..., 0]), "geo_feat": h[..., 1:]}
+        # exp in fp32 whatever the autocast state (activation.py:6-20 casts its input; `custom_fwd(cast_inputs=...)` only
+        # does so while autocast is ACTIVE, and the FFMLP output is fp16: exp(h > 11.09) overflows there)
+        return {"sigma": trunc_exp(h[..., 0].float()), "geo_feat": h[..., 1:]}
 
     def color(self, x, d, cal_lidar_color=False, mask=None, geo_feat=None, **kwargs):
         out_dim = self.out_lidar_color_dim if cal_lidar_color else self.out_color_dim

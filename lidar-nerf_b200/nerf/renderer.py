@@ -4,14 +4,23 @@
 
   * `run`       - the reference's dense sampling (num_steps uniform + upsample_steps importance samples), restated;
                   pure torch, runs on CPU (BASELINE config 1) and is checked against tests/golden/ref_py_run.npz;
-  * `run_cuda`  - `march_rays_train -> density/color -> composite_rays_train` on the sm_100a kernels, with the density
-                  grid / bitfield / step-counter state of SURVEY.md Appendix A kept on the module and refreshed every
-                  16 training calls (the unmodified Trainer never calls update_extra_state, SURVEY.md H12);
-  * `render(..., cuda_ray=True)` selects `run_cuda`; the default stays `run`, as in the reference.
+  * `run_cuda`  - `march_rays_train -> density/color -> composite_rays_train` on the sm_100a kernels op by op (B2
+                  wrappers + torch autograd), with the density grid / bitfield / step-counter state of SURVEY.md
+                  Appendix A kept on the module and refreshed every `grid_update_interval` (16) training calls (the
+                  unmodified Trainer never calls update_extra_state, SURVEY.md H12);
+  * `run_fused` - the same occupancy path as ONE autograd Function over the fused kernels (nerf/fused_render.py): what
+                  the training engine launches, reachable from `Trainer.train_step` (nerf/utils.py:716-724).
+`render()` picks the path.  The reference's CLI has no `cuda_ray` switch, so the default is
+decided here: on a CUDA device, for `cal_lidar_color=True`, `render()` takes `run_fused` when the network maps onto the
+fused kernels, else `run_cuda`; on the CPU (BASELINE config 1) or for the RGB branch it takes the reference's dense
+`run`.  `LNB_CUDA_RAY=dense|ops|fused` (environment) or `render(..., cuda_ray="dense"|"ops"|"fused"|True|False)`
+override.
 LiDAR specifics kept: fixed near = min_near_lidar, far = 81 x near (renderer.py:129-138); absolute depth
-(renderer.py:268; the kernels' relative depth gets `+ t0 * weights_sum`); no background blend.
+(renderer.py:268; the training kernels' depth is relative to the march start and gets `+ t0 * weights_sum`,
+SURVEY.md H2); no background blend.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -69,6 +78,9 @@ class NeRFRenderer(nn.Module):
         self.mean_count = 0
         self.local_step = 0
         self.cuda_ray_calls = 0
+        self.grid_update_interval = 16      # training calls between self-scheduled density-grid refreshes; 0 = the caller
+                                            # manages the grid (update_extra_state / a user-written bitfield)
+        self._fused = None                  # FusedLidarRender workspace (created on first use)
 
     def forward(self, x, d):
         raise NotImplementedError()
@@ -159,23 +171,29 @@ class NeRFRenderer(nn.Module):
         nears, fars = self._near_far(rays_o, rays_d, cal_lidar_color)
 
         if self.training:
-            if self.cuda_ray_calls % 16 == 0:          # self-scheduled grid refresh (Trainer never calls it)
-                self.update_extra_state()
-            self.cuda_ray_calls += 1
+            self._maybe_refresh_grid()
             counter = self.step_counter[self.local_step % 16]
             counter.zero_()
             self.local_step += 1
+            # the jitter is drawn HERE (not inside the wrapper) because the march start t0 = near + dt(near) * noise
+            # (raymarching.cu:375) is needed below and the kernel does not return it
+            noises = torch.rand(N, dtype=torch.float32, device=rays_o.device) if perturb else None
             xyzs, dirs, deltas, rays = rm.march_rays_train(rays_o, rays_d, self.bound, self.density_bitfield,
                                                            self.cascade, self.grid_size, nears, fars, counter,
                                                            self.mean_count, perturb, 128, force_all_rays, dt_gamma,
-                                                           max_steps)
+                                                           max_steps, noises)
             dens = self.density(xyzs)
             sigmas = dens.pop("sigma") * self.density_scale
             rgbs = self.color(xyzs, dirs, cal_lidar_color=cal_lidar_color, **dens).float()
             weights_sum, depth, image = rm.composite_rays_train(sigmas.float(), rgbs, deltas, rays, T_thresh, True)
-            # absolute depth: the kernels measure t from the (unperturbed) near plane onward only approximately -
-            # add the march start so the LiDAR loss compares against absolute range
-            depth = depth + nears * weights_sum
+            # the training kernel accumulates depth RELATIVE to the march start (raymarching.cu:640-646: `t` restarts at 0
+            # on the first sample): add t0 * weights_sum so the LiDAR loss compares against absolute range
+            t0 = nears
+            if perturb:
+                dt_min = 2 * math.sqrt(3) / max_steps
+                dt_max = 2 * math.sqrt(3) * (1 << (self.cascade - 1)) / self.grid_size
+                t0 = nears + torch.clamp(nears * dt_gamma, dt_min, dt_max) * noises
+            depth = depth + t0 * weights_sum
         else:
             weights_sum = torch.zeros(N, dtype=torch.float32, device=rays_o.device)
             depth = torch.zeros_like(weights_sum)
@@ -198,12 +216,64 @@ class NeRFRenderer(nn.Module):
                                   depth, image, 1e-2)
                 alive = alive[alive >= 0]
                 step += n_step
-            depth = depth + nears * weights_sum
+            # (no `+ near * weights_sum` here: rays_t starts at `nears` and the inference kernel accumulates absolute t,
+            # raymarching.cu:995-1025)
             image = image[:, : self.out_dim]
         if not cal_lidar_color:
             image = image + (1 - weights_sum).unsqueeze(-1) * (1 if bg_color is None else bg_color)
         return {"depth_lidar": depth.view(*prefix), "image_lidar": image.reshape(*prefix, self.out_dim),
                 "weights_sum_lidar": weights_sum}
+
+    def _maybe_refresh_grid(self):
+        """Self-scheduled density-grid refresh of the occupancy paths (the unmodified Trainer never calls
+        update_extra_state); `grid_update_interval = 0` turns it off."""
+        k = int(self.grid_update_interval)
+        if k > 0 and self.cuda_ray_calls % k == 0:
+            self.update_extra_state()
+        self.cuda_ray_calls += 1
+
+    def fused_unsupported_reason(self):
+        """None when `run_fused` can serve this network's LiDAR branch (subclasses that own the networks override)."""
+        return "this renderer has no field network"
+
+    def run_fused(self, rays_o, rays_d, cal_lidar_color=True, dt_gamma=0, perturb=False, max_steps=1024, T_thresh=1e-4,
+                  **kwargs):
+        """Occupancy march + fused field kernels + compositing as one autograd Function (nerf/fused_render.py)."""
+        if not cal_lidar_color:
+            raise RuntimeError("run_fused serves the LiDAR branch (cal_lidar_color=True) only")
+        from .fused_render import FusedLidarRender
+        if self._fused is None:
+            self._fused = FusedLidarRender(self)
+        self.out_dim = self.out_lidar_color_dim
+        prefix = rays_o.shape[:-1]
+        rays_o = rays_o.contiguous().view(-1, 3).float()
+        rays_d = rays_d.contiguous().view(-1, 3).float()
+        if self.training:
+            self._maybe_refresh_grid()
+        weights_sum, depth, image = self._fused(rays_o, rays_d, perturb=perturb, dt_gamma=dt_gamma, max_steps=max_steps,
+                                                T_thresh=T_thresh)
+        return {"depth_lidar": depth.view(*prefix), "image_lidar": image.reshape(*prefix, self.out_dim),
+                "weights_sum_lidar": weights_sum}
+
+    def _pick_path(self, rays_o, cal_lidar_color, cuda_ray):
+        if cuda_ray is None:
+            cuda_ray = os.environ.get("LNB_CUDA_RAY", "auto")
+        if cuda_ray is True:
+            cuda_ray = "ops"
+        if cuda_ray is False or cuda_ray in ("0", "dense", "off"):
+            return self.run
+        if cuda_ray == "ops":
+            return self.run_cuda
+        if cuda_ray == "fused":
+            why = self.fused_unsupported_reason() if cal_lidar_color else "RGB branch"
+            if why is not None:
+                raise RuntimeError(f"cuda_ray='fused' requested but the fused kernels cannot serve this network: {why}")
+            return self.run_fused
+        if cuda_ray != "auto":
+            raise ValueError(f"cuda_ray={cuda_ray!r}: choose from auto, dense, ops, fused")
+        if not rays_o.is_cuda or not cal_lidar_color:
+            return self.run
+        return self.run_fused if self.fused_unsupported_reason() is None else self.run_cuda
 
     @torch.no_grad()
     def update_extra_state(self, decay=0.95):
@@ -226,9 +296,9 @@ class NeRFRenderer(nn.Module):
         self.local_step = 0
 
     # ------------------------------------------------------------------------------------------------ entry point
-    def render(self, rays_o, rays_d, cal_lidar_color=False, staged=False, max_ray_batch=4096, cuda_ray=False,
+    def render(self, rays_o, rays_d, cal_lidar_color=False, staged=False, max_ray_batch=4096, cuda_ray=None,
                **kwargs):
-        fn = self.run_cuda if cuda_ray else self.run
+        fn = self._pick_path(rays_o, cal_lidar_color, cuda_ray)
         if not staged:
             return fn(rays_o, rays_d, cal_lidar_color=cal_lidar_color, **kwargs)
         B, N = rays_o.shape[:2]

@@ -78,7 +78,9 @@ class _MarchTrain(Function):
     @staticmethod
     @_fwd32
     def forward(ctx, rays_o, rays_d, bound, density_bitfield, C, H, nears, fars, step_counter=None, mean_count=-1,
-                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024):
+                perturb=False, align=-1, force_all_rays=False, dt_gamma=0, max_steps=1024, noises=None):
+        # `noises` (extension, optional, trailing): the per-ray jitter in [0,1) the caller drew itself because it needs
+        # the march start t0 = near + dt * noise afterwards; None = drawn here like the reference (raymarching.py:250-253)
         rays_o, rays_d = _rays_2d(rays_o), _rays_2d(rays_d)
         bitfield = (density_bitfield if density_bitfield.is_cuda else density_bitfield.cuda()).contiguous()
         dev, dt = rays_o.device, rays_o.dtype
@@ -98,7 +100,9 @@ class _MarchTrain(Function):
         rays = torch.empty(n, 3, dtype=torch.int32, device=dev)
         if step_counter is None:
             step_counter = torch.zeros(2, dtype=torch.int32, device=dev)
-        noises = torch.rand(n, dtype=dt, device=dev) if perturb else torch.zeros(n, dtype=dt, device=dev)
+        if noises is None:
+            noises = torch.rand(n, dtype=dt, device=dev) if perturb else torch.zeros(n, dtype=dt, device=dev)
+        noises = noises.to(dt).contiguous()
 
         _backend.march_rays_train(rays_o, rays_d, bitfield, bound, dt_gamma, max_steps, n, C, H, budget,
                                   nears.contiguous(), fars.contiguous(), xyzs, dirs, deltas, rays, step_counter,

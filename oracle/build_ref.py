@@ -87,7 +87,42 @@ def build(name):
     return ok
 
 
+PYREF = os.path.join(OUT, "pyref")
+PY_TREES = ["lidarnerf", "extern"]          # packages the entry script imports (pure Python; .cu/.cpp are not touched here)
+PY_FILES = ["main_lidarnerf.py"]
+
+
+def build_pyref():
+    """Byte-compile the reference's UNMODIFIED Python (Trainer, datasets, entry script) from where it lies into
+    SOURCELESS .pyc files under oracle/_ref/pyref/ - a binary artefact with the same status as the extension .so files
+    above: git-ignored, travels to the GPU box, test infrastructure only.  `tests/test_reference_trainer.py` puts that
+    directory on sys.path so the reference's own `Trainer.train_step` / `main_lidarnerf.main()` drive this library's
+    kernels through `lidar_nerf_b200.compat.install()`.  No reference source text enters the repository."""
+    import py_compile
+    if not os.path.isdir(REF):
+        print(f"[build_ref] {REF} not present (GPU box?) - skipping pyref")
+        return False
+    n = 0
+    todo = [(os.path.join(REF, f), os.path.join(PYREF, f + "c")) for f in PY_FILES]
+    for tree in PY_TREES:
+        for root, _dirs, files in os.walk(os.path.join(REF, tree)):
+            for f in files:
+                if f.endswith(".py"):
+                    src = os.path.join(root, f)
+                    todo.append((src, os.path.join(PYREF, os.path.relpath(src, REF) + "c")))
+    for src, dst in todo:
+        if os.path.exists(dst) and os.path.getmtime(dst) >= os.path.getmtime(src):
+            continue
+        os.makedirs(os.path.dirname(dst), exist_ok=True)
+        # dfile: tracebacks name the reference path, not a path inside this repo
+        py_compile.compile(src, cfile=dst, dfile=os.path.relpath(src, REF), doraise=True,
+                           invalidation_mode=py_compile.PycInvalidationMode.UNCHECKED_HASH)
+        n += 1
+    print(f"[build_ref] pyref: {len(todo)} modules ({n} compiled now) -> {PYREF}")
+    return True
+
+
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(EXTS)
-    res = {n: build(n) for n in names}
+    names = sys.argv[1:] or (list(EXTS) + ["pyref"])
+    res = {n: (build_pyref() if n == "pyref" else build(n)) for n in names}
     sys.exit(0 if all(res.values()) else 1)

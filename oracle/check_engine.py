@@ -63,6 +63,14 @@ def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2):
     return eng, gpu, cpu
 
 
+def _record(name, **vals):
+    try:
+        from conftest import record_parity      # tests/ on sys.path: only under pytest
+        record_parity(name, **vals)
+    except Exception:
+        pass
+
+
 def compare(gpu, cpu, n_table, verbose=True):
     """Raises AssertionError with a diagnostic when the fused step disagrees with the restatement."""
     np.testing.assert_array_equal(gpu["counts"], cpu["counts"], err_msg="per-ray sample counts")
@@ -79,4 +87,6 @@ def compare(gpu, cpu, n_table, verbose=True):
         cos = float(a @ b / max(np.linalg.norm(a) * np.linalg.norm(b), 1e-30))
         if verbose:
             print(f"[check_engine] grad {name}: |g|={np.linalg.norm(b):.4e} rel.err={rel:.3e} cos={cos:.6f}")
-        assert rel < 3e-2 and cos > 0.999, f"gradient of {name} disagrees: rel={rel:.3e} cos={cos:.6f}"
+        _record(f"check_engine.compare[{name}]", rel=rel, one_minus_cos=1 - cos)
+        # observed on B200: rel 4e-5 .. 3e-4 (fp16 activations / fast-math exp, fp32 accumulation on both sides)
+        assert rel < 2e-3 and cos > 0.99999, f"gradient of {name} disagrees: rel={rel:.3e} cos={cos:.6f}"

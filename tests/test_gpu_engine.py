@@ -34,6 +34,56 @@ def test_unfused_chain_matches_cpu_restatement_and_fused_kernels():
         assert (ids[off:off + cnt] == n).all()
 
 
+def test_persistent_gather_field_kernel_is_bit_identical_to_the_two_kernel_forward():
+    """lnb_field_fused_forward (gather warps feeding the tensor-core MLPs inside ONE persistent kernel, weights staged by
+    the TMA engine) == lnb_grid_encode_forward_ex -> lnb_field_forward, bit for bit, on everything the step keeps."""
+    from oracle import check_engine
+    out = {}
+    for fused_gather in (False, True):
+        for n_rays, over in ((256, {}), (1024, dict(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024))):
+            cfg = check_engine.small_config(fused_gather=fused_gather, perturb=False, **over)
+            if n_rays == 256:
+                eng, _, _ = check_engine.run_pair(n_rays=n_rays, device=DEV, cfg=cfg, seed=7)
+            else:
+                eng = _run_engine_only(cfg, n_rays)
+            assert eng.fused_gather == fused_gather
+            n = int(eng.counter[0])
+            assert n > 1000
+            out[(fused_gather, n_rays)] = dict(enc=eng.enc[:n].clone(), sigma=eng.sigma[:n].clone(), rgb=eng.rgb[:n].clone(),
+                                               sig_out=eng.sig_out[:n].clone(), fb_s=eng.fb_sigma[:, :n].clone(),
+                                               fb_h=eng.fb_head[:, :n].clone(), G=eng.G.clone(), loss=float(eng.loss_acc))
+    for n_rays in (256, 1024):
+        a, b = out[(True, n_rays)], out[(False, n_rays)]
+        for k in ("enc", "sigma", "rgb", "sig_out", "fb_s", "fb_h"):
+            assert torch.equal(a[k], b[k]), (n_rays, k, float((a[k].float() - b[k].float()).abs().max()))
+        assert a["loss"] == b["loss"]
+        # identical forward -> identical inputs of the backward kernels; only the fp32 atomics' order differs
+        assert float((a["G"] - b["G"]).norm() / b["G"].norm()) < 1e-5
+
+
+def _run_engine_only(cfg, n_rays, seed=11):
+    """A forward/backward on random rays through a clumpy grid without the CPU restatement (larger sizes)."""
+    from lidar_nerf_b200.nerf.engine import LidarFieldEngine
+    g = torch.Generator().manual_seed(seed)
+    eng = LidarFieldEngine(cfg, n_rays, device=DEV, sample_budget=n_rays * 300)
+    eng.P[:eng.n_table].copy_((torch.rand(eng.n_table, generator=g) - 0.5).to(DEV))
+    eng.Ph.copy_(eng.P.to(torch.float16))
+    d = torch.randn(n_rays, 3, generator=g)
+    d = d / d.norm(dim=-1, keepdim=True)
+    o = (torch.rand(1, 3, generator=g) * 0.04 - 0.02).expand(n_rays, 3)
+    gt = torch.stack([(torch.rand(n_rays, generator=g) < 0.9).float(), torch.rand(n_rays, generator=g),
+                      torch.rand(n_rays, generator=g) * 0.75 + 0.05], -1)
+    bits = (torch.rand(cfg.cascade * cfg.grid_size ** 3 // 4096, generator=g) < 0.2).repeat_interleave(4096)
+    packed = torch.from_numpy(np.packbits(bits.numpy().reshape(-1, 8), axis=1, bitorder="little").reshape(-1))
+    eng.bitfield.copy_(packed.to(DEV))
+    eng.set_batch(o.contiguous().to(DEV), d.to(DEV), gt.to(DEV))
+    eng.G.zero_()
+    eng.loss_acc.zero_()
+    eng._forward_backward()
+    torch.cuda.synchronize()
+    return eng
+
+
 def test_fused_composite_step_equals_the_three_kernel_chain():
     """lnb_lidar_composite_step = composite forward + lidar_loss + composite backward (+ the zero fill it removes)."""
     from oracle import check_engine
@@ -128,7 +178,9 @@ def test_fused_step_matches_step_built_from_reference_cuda_kernels():
         cos = float((a @ b) / (a.norm() * b.norm()))
         rel = float((a - b).norm() / b.norm())
         # the reference accumulates both gradients in fp16 (half2 atomics, fp16 split-K); ours in fp32
-        assert cos > 0.995 and rel < 0.1, (name, cos, rel)
+        from conftest import record_parity
+        record_parity(f"fused_vs_reference_cuda_step[{name}]", rel=rel, one_minus_cos=1 - cos)
+        assert cos > 0.999 and rel < 3e-2, (name, cos, rel)
 
 
 def test_graph_replay_equals_eager():
