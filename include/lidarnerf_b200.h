@@ -335,6 +335,11 @@ int lnb_lidar_rays(const float *pose, const int32_t *inds, uint32_t N, uint32_t 
  * and enters the head's first layer as a per-ray bias; only the 15 geo features go through the tensor cores.
  * Layer shapes as lnb_ffmlp_*: hidden = 64, outputs padded to 16, ReLU, no biases.
  * ---------------------------------------------------------------------------------------- */
+/* Direction encoding of the head input.  Every `degree` argument of the lnb_field_* entry points takes either a
+ * frequency degree (freqencoder.cu:34-61: 3 + 6*degree columns; the LiDAR head of network.py:83 uses 12) or
+ * LNB_DIR_SH(deg): real spherical harmonics of that degree (shencoder.cu:31-277: deg*deg columns; the direction
+ * encoder of network.py:64 / network_tcnn.py:74-80, degree 4), evaluated once per ray like the frequency terms. */
+#define LNB_DIR_SH(deg) (0x100u | (uint32_t)(deg))
 /* LNB_OK when the fused kernels implement this configuration (else use the unfused chain) */
 int lnb_field_supported(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
                         uint32_t degree, uint32_t hidden);

@@ -35,6 +35,15 @@ __device__ __forceinline__ float clampf(float x, float lo, float hi) { return fm
 
 __device__ __forceinline__ unsigned lane_id() { return threadIdx.x & 31u; }
 
+// Width of the head's direction encoding for a `degree` argument of the lnb_field_* entry points (LNB_DIR_SH, see the
+// header): frequency 3 + 6 deg, spherical harmonics deg^2.
+__host__ __device__ __forceinline__ uint32_t dir_code_width(uint32_t code) {
+    return (code & 0x100u) ? (code & 0xffu) * (code & 0xffu) : 3u + 6u * code;
+}
+__host__ __device__ __forceinline__ bool dir_code_valid(uint32_t code) {
+    return (code & 0x100u) ? ((code & 0xffu) == 4u) : (code >= 1u && code <= 20u);     // SH: degree 4 only (16 columns)
+}
+
 // Number of rows a sample-parallel kernel has to process: all B of them, or - when the caller passes the device
 // counter the march kernel filled - the produced samples rounded up to a 128-row tile.  Lets the training step
 // size its buffers generously (no dropped rays) while the work tracks the real sample count without a host sync.

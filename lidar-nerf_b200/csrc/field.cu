@@ -29,6 +29,47 @@ struct FieldShape {
 // per-ray direction terms:  ray_enc[n] = fp16([freq_enc(dir_n) | 0...])  (freqencoder.cu:34-61 layout),
 //                           ray_bias[n][h] = sum_{j<nfreq} W_in[h][j] * ray_enc[n][j]   (fp32)
 // -----------------------------------------------------------------------------------------------------
+// Real spherical harmonics of degree 4 (16 values) by the recurrence of csrc/shencoder.cu (same arithmetic, so the fused
+// head sees exactly what lnb_sh_encode_forward would produce): Y_{l,+-m} = N_l^m Q_l^m(z) Re/Im (x + i y)^m.
+__device__ __forceinline__ void sh4_eval(float x, float y, float z, float (&o)[16]) {
+    constexpr int DEG = 4;
+    const float norm[DEG][DEG] = {
+        {0.28209479177387814f, 0.f, 0.f, 0.f},
+        {0.48860251190291992f, -0.48860251190291998f, 0.f, 0.f},
+        {0.63078313050504009f, -0.36418281019735976f, 0.18209140509867988f, 0.f},
+        {0.7463526651802308f, -0.3046971996429772f, 0.096353714754685155f, -0.039336239328442907f}};
+    float A[DEG + 1], Bm[DEG + 1];
+    A[0] = 1.f, Bm[0] = 0.f;
+#pragma unroll
+    for (int m = 1; m <= DEG; ++m) {
+        A[m] = x * A[m - 1] - y * Bm[m - 1];
+        Bm[m] = x * Bm[m - 1] + y * A[m - 1];
+    }
+    float Q[DEG][DEG + 1];
+#pragma unroll
+    for (int l = 0; l < DEG; ++l)
+#pragma unroll
+        for (int m = 0; m <= DEG; ++m) Q[l][m] = 0.f;
+    float dfact = 1.f;
+#pragma unroll
+    for (int m = 0; m < DEG; ++m) {
+        if (m > 0) dfact *= (float)(2 * m - 1);
+        Q[m][m] = dfact;
+        if (m + 1 < DEG) Q[m + 1][m] = (float)(2 * m + 1) * z * dfact;
+#pragma unroll
+        for (int l = m + 2; l < DEG; ++l)
+            Q[l][m] = ((float)(2 * l - 1) * z * Q[l - 1][m] - (float)(l + m - 1) * Q[l - 2][m]) * (1.0f / (float)(l - m));
+    }
+#pragma unroll
+    for (int l = 0; l < DEG; ++l)
+#pragma unroll
+        for (int m = 0; m <= l; ++m) {
+            const float nq = norm[l][m] * Q[l][m];
+            o[l * l + l + m] = nq * A[m];
+            if (m > 0) o[l * l + l - m] = nq * Bm[m];
+        }
+}
+
 constexpr uint32_t kRaysPerBlock = 16;   // 4 rays at a time (one per 64-thread group), 4 rounds
 __global__ void __launch_bounds__(256)
 k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_head, uint32_t N, uint32_t deg,
@@ -37,7 +78,8 @@ k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_h
     // conflicts when thread h walks row h) and reused for kRaysPerBlock rays
     __shared__ __align__(16) __half w[kHid * (128 + 2)];
     __shared__ float e[4][128];
-    const uint32_t nfreq = 3 + 6 * deg;
+    const uint32_t nfreq = dir_code_width(deg);      // columns of the direction encoding (frequency or SH, LNB_DIR_SH)
+    const bool sh = (deg & 0x100u) != 0;
     const uint32_t pitch = in_pad + 2;
     for (uint32_t q = threadIdx.x; q < kHid * in_pad / 2; q += 256) {       // in_pad is even: copy half2 words
         const uint32_t r = (2 * q) / in_pad, c = 2 * q - r * in_pad;
@@ -51,10 +93,18 @@ k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_h
         float d[3] = {0.f, 0.f, 0.f};
         if (live) d[0] = rays_d[n * 3], d[1] = rays_d[n * 3 + 1], d[2] = rays_d[n * 3 + 2];
         __syncthreads();   // weights staged (first round) / previous round's e[] fully consumed
+        float shv[16];
+        if (live && sh && h < 16) sh4_eval(d[0], d[1], d[2], shv);
         if (live)
             for (uint32_t j = h; j < in_pad; j += 64) {
                 float v = 0.f;
-                if (j < 3) {
+                if (sh) {
+                    if (j < 16) {
+#pragma unroll
+                        for (uint32_t q = 0; q < 16; ++q)
+                            if (q == j) v = shv[q];
+                    }
+                } else if (j < 3) {
                     v = d[j];
                 } else if (j < nfreq) {
                     const uint32_t f = (j - 3) / 6, r = (j - 3) % 6, a = r % 3;
@@ -335,7 +385,8 @@ int make_field_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_p
     if (rc != LNB_OK) return rc;
     rc = make_shape(head_in_pad, head_layers, &fs->h);
     if (rc != LNB_OK) return rc;
-    fs->nfreq = 3 + 6 * degree;
+    if (!dir_code_valid(degree)) return LNB_ERR_UNSUPPORTED;
+    fs->nfreq = dir_code_width(degree);
     if (fs->nfreq + 15 > head_in_pad) return LNB_ERR_INVALID_ARGUMENT;
     fs->geo_tile = fs->nfreq / 64;
     fs->geo_off = fs->nfreq % 64;
@@ -366,14 +417,15 @@ int lnb_field_supported(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_i
     FieldShape fs;
     int rc = make_field_shape(enc_dim, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
     if (rc != LNB_OK) return rc;
-    if (!(fs.geo_off % 32 + 15 <= 32 && (fs.geo_off == 11 || fs.geo_off == 39))) return LNB_ERR_UNSUPPORTED;
+    if (!(fs.geo_off % 32 + 15 <= 32 && (fs.geo_off == 11 || fs.geo_off == 39 || fs.geo_off == 16))) return LNB_ERR_UNSUPPORTED;
     return LNB_OK;
 }
 
 int lnb_field_ray_terms(const float *rays_d, const void *w_head, uint32_t N, uint32_t degree, uint32_t in_pad,
                         void *ray_enc, float *ray_bias, lnb_stream_t stream) {
     if (!rays_d || !w_head || !ray_enc || !ray_bias) return LNB_ERR_INVALID_ARGUMENT;
-    if (in_pad > 128 || in_pad % 8 != 0 || 3 + 6 * degree + 15 > in_pad) return LNB_ERR_INVALID_ARGUMENT;
+    if (!dir_code_valid(degree)) return LNB_ERR_UNSUPPORTED;
+    if (in_pad > 128 || in_pad % 8 != 0 || dir_code_width(degree) + 15 > in_pad) return LNB_ERR_INVALID_ARGUMENT;
     if (N == 0) return LNB_OK;
     k_ray_dir_terms<<<(N + kRaysPerBlock - 1) / kRaysPerBlock, 256, 0, as_stream(stream)>>>(rays_d, static_cast<const __half *>(w_head), N, degree, in_pad,
                                                       static_cast<__half *>(ray_enc), ray_bias);
@@ -443,6 +495,7 @@ static int field_head_backward_impl(const float *g_rgb, const float *rgb, const 
     int rc2;
     if (fs.geo_off == 11) rc2 = launch_mlp_bwd<true, 0, 11>(a, (uint32_t)sm_count_field(), as_stream(stream));        // degree 12
     else if (fs.geo_off == 39) rc2 = launch_mlp_bwd<true, 32, 7>(a, (uint32_t)sm_count_field(), as_stream(stream));   // degree 6
+    else if (fs.geo_off == 16) rc2 = launch_mlp_bwd<true, 0, 16>(a, (uint32_t)sm_count_field(), as_stream(stream));   // SH degree 4
     else return LNB_ERR_UNSUPPORTED;
     if (rc2 != LNB_OK) return rc2;
     count_launch();

@@ -22,6 +22,8 @@
 // bit-for-bit on the saved activations.
 //
 // Reference behaviour: gridencoder.cu:95-199 (gather), ffmlp.cu:460-576 (MLP), network.py:162-237 (wiring).
+#include <cstdlib>
+
 #include "common.cuh"
 #include "grid_common.cuh"
 #include "mlp_tiles.cuh"
@@ -31,13 +33,18 @@ namespace {
 
 constexpr uint32_t kGatherWarps = 16;
 constexpr uint32_t kGatherThreads = kGatherWarps * 32;
-constexpr uint32_t kGroups = 2;                        // tiles in flight in the MLP part (epilogue groups)
+constexpr uint32_t kGroups = 2;                        // epilogue groups (128 threads, thread = tile row)
+constexpr uint32_t kSlotsPerGroup = 2;                 // tiles a group keeps in flight, processed phase by phase in turn
+constexpr uint32_t kSlots = kGroups * kSlotsPerGroup;  // tiles in flight in the MLP part of one CTA
 constexpr uint32_t kGroupThreads = 128;
 constexpr uint32_t kEpiWarp0 = kGatherWarps;           // first epilogue warp (multiple of 4: TMEM lane quadrants)
 constexpr uint32_t kMmaWarpIdx = kEpiWarp0 + kGroups * 4;
 constexpr uint32_t kFusedThreads = (kMmaWarpIdx + 1) * 32;      // 800
 constexpr uint32_t kStages = 3;                        // operand tiles between the gather and the first MLP layer
-constexpr uint32_t kTmemColsPerGroup = 128;            // [0,64) hidden accumulator, [64,80) output accumulator
+constexpr uint32_t kTmemColsPerSlot = 128;             // [0,64) hidden accumulator, [64,80) output accumulator
+constexpr uint32_t kRing = 4;                          // gather batches (32 samples x 8 corners) in flight per warp
+constexpr uint32_t kScratchPerWarp = kRing * 8 * 32 * 4;        // cp.async landing zone: [batch][corner][lane] x 4 B
+constexpr uint32_t kCoordBufs = 3;
 
 struct FusedShape {
     uint32_t enc_dim;        // L * C (multiple of 16, <= 64)
@@ -67,6 +74,8 @@ struct FusedArgs {
     float density_scale;
     __half *enc, *fb_s, *sig_out, *fb_h;
     float *sigma, *rgb;
+    uint32_t dbg;     // diagnostics only (LNB_FUSED_DBG, scripts/diag_fused_fwd.py): bit 0 = gather without table loads,
+                      // bit 1 = no saved-activation / enc stores, bit 2 = epilogue skips the per-layer math
 };
 
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
@@ -146,6 +155,19 @@ __device__ __forceinline__ void row_relu_pack(uint32_t d_row, const float4 *__re
     }
 }
 
+// four-byte asynchronous global -> shared copy (LDGSTS): a gathered table row lands in shared memory without occupying
+// a register while it is in flight
+__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(uint32_t n) {      // n = groups that may still be in flight
+    if (n == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
+    else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
+    else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
+    else asm volatile("cp.async.wait_group 3;" ::: "memory");
+}
+
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_field_fused_fwd(const FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -160,25 +182,27 @@ k_field_fused_fwd(const FusedArgs a) {
     const uint32_t s_wh_out = s_wh_hid + fs.n_hid_h * kWTileBytes;
     const uint32_t wbytes = weight_image_bytes(fs);
     const uint32_t s_x0 = sbase + wbytes;                          // kStages operand tiles written by the gather
-    const uint32_t s_h0 = s_x0 + kStages * kTileBytes;             // one activation operand tile per group
-    const uint32_t s_in0 = s_h0 + kGroups * kTileBytes;            // 2 x [128][3] coordinates in [0,1]
-    const uint32_t s_bar = s_in0 + 2 * kRows * 3 * 4;
+    const uint32_t s_h0 = s_x0 + kStages * kTileBytes;             // one activation operand tile per slot
+    const uint32_t s_sc0 = s_h0 + kSlots * kTileBytes;             // gather landing zones, one per gather warp
+    const uint32_t s_in0 = s_sc0 + kGatherWarps * kScratchPerWarp; // kCoordBufs x [128][3] coordinates in [0,1]
+    const uint32_t s_bar = s_in0 + kCoordBufs * kRows * 3 * 4;
     const uint32_t bar_xfull = s_bar, bar_xempty = bar_xfull + 8 * kStages, bar_ready = bar_xempty + 8 * kStages;
-    const uint32_t bar_done = bar_ready + 8 * kGroups, bar_w = bar_done + 8 * kGroups, s_slot = bar_w + 8;
+    const uint32_t bar_done = bar_ready + 8 * kSlots, bar_w = bar_done + 8 * kSlots, s_slot = bar_w + 8;
     float *s_in = reinterpret_cast<float *>(smem_raw + (s_in0 - smem_u32(smem_raw)));
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31u;
-    constexpr uint32_t kTmemCols = kGroups * kTmemColsPerGroup <= 256 ? 256u : 512u;
+    constexpr uint32_t kTmemCols = 512;
+    static_assert(kSlots * kTmemColsPerSlot <= kTmemCols, "tensor memory");
 
     if (warp == kMmaWarpIdx) tmem_alloc(s_slot, kTmemCols);
     if (threadIdx.x == 0) {
         for (uint32_t s = 0; s < kStages; ++s) {
-            mbar_init(bar_xfull + 8 * s, kGatherWarps);
-            mbar_init(bar_xempty + 8 * s, 1 + kGroupThreads);
+            mbar_init(bar_xfull + 8 * s, kGatherWarps);           // one arrival per gather warp
+            mbar_init(bar_xempty + 8 * s, 1 + 4);                 // tcgen05.commit + one arrival per epilogue warp
         }
-        for (uint32_t g = 0; g < kGroups; ++g) {
-            mbar_init(bar_ready + 8 * g, kGroupThreads);
-            mbar_init(bar_done + 8 * g, 1);
+        for (uint32_t q = 0; q < kSlots; ++q) {
+            mbar_init(bar_ready + 8 * q, 4);                      // one arrival per epilogue warp of the owning group
+            mbar_init(bar_done + 8 * q, 1);
         }
         mbar_init(bar_w, 1);
         mbar_init_fence();
@@ -199,194 +223,262 @@ k_field_fused_fwd(const FusedArgs a) {
 
     if (warp < kGatherWarps) {
         // ======================= GATHER: warp <-> level =======================
-        // register budget: the 16 gather warps give registers back, the 8 epilogue warps (a 64-column accumulator row
-        // per thread) take them (setmaxnreg works per warpgroup = 4 consecutive warps).  Pool arithmetic: the CTA is
-        // launched with 72 registers x 800 threads; 512 gather threads release 16 each = 8192 = 256 epilogue threads x 32
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
+        // Register budget (setmaxnreg works per warpgroup = 4 consecutive warps): the CTA is launched with 72 registers x
+        // 800 threads; the gathered rows travel global -> shared by cp.async (no register per load in flight), so the 512
+        // gather threads can hand 24 registers each (72 -> 48) to the 256 epilogue threads (72 -> 120; a 64-column accumulator row per thread).
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
         const uint32_t tid = threadIdx.x;
         constexpr uint32_t D = 3, C = 2;
-        // level-uniform quantities, once per kernel (the warp keeps its levels for every tile)
-        const uint32_t level0 = warp;
+        const uint32_t s_sc = s_sc0 + warp * kScratchPerWarp;
+        const uint32_t nlv = warp < a.L ? (a.L - warp + kGatherWarps - 1) / kGatherWarps : 0;   // levels of this warp
+        const uint32_t per_tile = nlv * (kRows / 32);                                            // batches per tile
+        const uint32_t n_items = n_my * per_tile;
+        // level-uniform quantities of the warp's first level, once per kernel
         LevelGeo g0 = {};
         LevelIndex<D> li0 = {};
-        if (level0 < a.L) {
-            g0 = level_geo(a.offsets, level0, a.S, a.H);
+        if (nlv > 0) {
+            g0 = level_geo(a.offsets, warp, a.S, a.H);
             li0 = level_index<D>(g0, 0u, false);
         }
-        auto stage_coords = [&](uint32_t k, uint32_t buf) {
-            if (tid < kRows * 3) {
+        auto stage_coords = [&](uint32_t k) {
+            if (tid < kRows * 3 && k < n_my) {
                 const size_t tile = blockIdx.x + (size_t)k * gridDim.x;
                 float x = __ldg(a.xyz + tile * kRows * 3 + tid);
                 if (a.norm.x != 0.f) x = (x + a.norm.x) * a.norm.y;
-                s_in[buf * kRows * 3 + tid] = x;
+                s_in[(k % kCoordBufs) * kRows * 3 + tid] = x;
             }
         };
-        if (n_my > 0) stage_coords(0, 0);
-        for (uint32_t k = 0; k < n_my; ++k) {
-            const uint32_t stage = k % kStages, use = k / kStages, buf = k & 1u;
-            named_bar(1, kGatherThreads);                   // s_in[buf] complete; everybody is done with s_in[buf ^ 1]
-            if (k + 1 < n_my) stage_coords(k + 1, buf ^ 1u);
-            if (use > 0) mbar_wait(bar_xempty + 8 * stage, (use - 1) & 1u);
-            const uint32_t s_x = s_x0 + stage * kTileBytes;
-            const float *in = s_in + buf * kRows * 3;
-            for (uint32_t level = level0; level < a.L; level += kGatherWarps) {
-                LevelGeo g = g0;
-                LevelIndex<D> li = li0;
-                if (level != level0) {
-                    g = level_geo(a.offsets, level, a.S, a.H);
-                    li = level_index<D>(g, 0u, false);
-                }
-                const __half *__restrict__ tab = a.table + (size_t)g.table_offset * C;
+        // item -> (tile k, level, sample group); the cell of this lane's sample on that level
+        auto locate_item = [&](uint32_t item, uint32_t &k, uint32_t &level, uint32_t &sl, LevelGeo &g, LevelIndex<D> &li) -> Cell<D> {
+            k = item / per_tile;
+            const uint32_t rem = item - k * per_tile;
+            const uint32_t lv = rem >> 2, grp = rem & 3u;
+            level = warp + lv * kGatherWarps;
+            g = g0, li = li0;
+            if (lv != 0) {
+                g = level_geo(a.offsets, level, a.S, a.H);
+                li = level_index<D>(g, 0u, false);
+            }
+            sl = grp * 32 + lane;
+            const float *in = s_in + (k % kCoordBufs) * kRows * 3 + sl * D;
+            float v[D];
+            bool inside = true;
 #pragma unroll
-                for (uint32_t grp = 0; grp < kRows / 32; ++grp) {
-                    const uint32_t sl = grp * 32 + lane;
-                    float v[D];
-                    bool inside = true;
+            for (uint32_t d = 0; d < D; ++d) {
+                v[d] = in[d];
+                if (v[d] < 0 || v[d] > 1) inside = false;
+            }
+            return locate_unit<D>(v, inside, g, false, 0u);
+        };
+        auto issue = [&](uint32_t item) {
+            uint32_t k, level, sl;
+            LevelGeo g;
+            LevelIndex<D> li;
+            const Cell<D> cell = locate_item(item, k, level, sl, g, li);
+            if (cell.inside && !(a.dbg & 1u)) {
+                const __half *__restrict__ tab = a.table + (size_t)g.table_offset * C;
+                const CornerRows<D> cr(li, cell.base);
+                const uint32_t dst = s_sc + ((item % kRing) * 8u * 32u + lane) * 4u;
+#pragma unroll
+                for (uint32_t corner = 0; corner < 8; ++corner) {
+                    uint32_t row;
+                    if (li.generic) {
+                        uint32_t pp[D];
+#pragma unroll
+                        for (uint32_t d = 0; d < D; ++d) pp[d] = cell.base[d] + ((corner >> d) & 1u);
+                        row = cell_row<D>(pp, 0u, false, g);
+                    } else {
+                        row = cr.row(corner);
+                    }
+                    cp_async4(dst + corner * 128u, tab + (size_t)row * C);
+                }
+            }
+            cp_async_commit();
+        };
+        auto consume = [&](uint32_t item, uint32_t s_x) {
+            uint32_t k, level, sl;
+            LevelGeo g;
+            LevelIndex<D> li;
+            const Cell<D> cell = locate_item(item, k, level, sl, g, li);
+            // sum over the 8 corners, accumulated in fp16 in corner order exactly like interp_corners() / the reference
+            // (gridencoder.cu:173-199)
+            __half res[C];
+            res[0] = res[1] = __float2half_rn(0.f);
+            if (cell.inside && !(a.dbg & 1u)) {
+                const uint32_t src = s_sc + ((item % kRing) * 8u * 32u + lane) * 4u;
+                uint32_t raw[8];
+#pragma unroll
+                for (uint32_t corner = 0; corner < 8; ++corner) raw[corner] = lds32(src + corner * 128u);
+#pragma unroll
+                for (uint32_t corner = 0; corner < 8; ++corner) {
+                    float w = 1;
 #pragma unroll
                     for (uint32_t d = 0; d < D; ++d) {
-                        v[d] = in[sl * D + d];
-                        if (v[d] < 0 || v[d] > 1) inside = false;
+                        if ((corner & (1u << d)) == 0) w *= 1 - cell.frac[d];
+                        else w *= cell.frac[d];
                     }
-                    const Cell<D> cell = locate_unit<D>(v, inside, g, false, 0u);
-                    __half res[C];
-                    res[0] = res[1] = __float2half_rn(0.f);
-                    if (cell.inside) {
-                        if (li.generic) interp_corners<__half, D, C, true>(cell, g, li, 0u, false, tab, res);
-                        else interp_corners<__half, D, C, false>(cell, g, li, 0u, false, tab, res);
-                    }
-                    sts32(elem_addr(s_x, sl, level * C), (uint32_t)__half_as_ushort(res[0]) | ((uint32_t)__half_as_ushort(res[1]) << 16));
+                    const __half2 hv = *reinterpret_cast<const __half2 *>(&raw[corner]);
+                    res[0] = __float2half_rn(__half2float(res[0]) + w * __low2float(hv));
+                    res[1] = __float2half_rn(__half2float(res[1]) + w * __high2float(hv));
                 }
+            }
+            sts32(elem_addr(s_x, sl, level * C), (uint32_t)__half_as_ushort(res[0]) | ((uint32_t)__half_as_ushort(res[1]) << 16));
+        };
+
+        stage_coords(0);
+        stage_coords(1);
+        uint32_t issued = 0;
+        for (uint32_t k = 0; k < n_my; ++k) {
+            const uint32_t stage = k % kStages, use = k / kStages;
+            // coordinates of tiles k and k + 1 are complete (staged one / two tiles ago); every warp has finished tile
+            // k - 1, whose coordinate buffer now takes tile k + 2
+            named_bar(1, kGatherThreads);
+            stage_coords(k + 2);
+            if (k == 0)
+                for (; issued < min(n_items, kRing - 1); ++issued) issue(issued);
+            if (use > 0) mbar_wait(bar_xempty + 8 * stage, (use - 1) & 1u);
+            const uint32_t s_x = s_x0 + stage * kTileBytes;
+            for (uint32_t j = 0; j < per_tile; ++j) {
+                const uint32_t item = k * per_tile + j;
+                if (issued < n_items) issue(issued++);       // keep kRing - 1 batches ahead of the one consumed next
+                cp_async_wait_pending(issued - item - 1);
+                consume(item, s_x);
             }
             fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
             __syncwarp();
             if (lane == 0) mbar_arrive(bar_xfull + 8 * stage);
         }
     } else if (warp < kMmaWarpIdx) {
-        // ======================= EPILOGUE groups: thread = tile row =======================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 104;");
+        // ======================= EPILOGUE groups: thread = tile row, two tiles in flight per group =======================
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const uint32_t g = (warp - kEpiWarp0) >> 2;
-        const uint32_t row = (warp & 3u) * 32u + lane;     // = TMEM lane (warp % 4 selects the 32-lane quadrant)
-        const uint32_t lane_sel = ((warp & 3u) * 32u) << 16;
-        const uint32_t d_hid = tmem + g * kTmemColsPerGroup + lane_sel;
-        const uint32_t d_out = d_hid + 64;
-        const uint32_t s_h = s_h0 + g * kTileBytes;
-        const uint32_t ready = bar_ready + 8 * g, done = bar_done + 8 * g;
-        uint32_t par = 0;
-        if (g < n_my) mbar_arrive(ready);                   // tensor memory of this group is free: first tile may start
-        for (uint32_t k = g; k < n_my; k += kGroups) {
-            const uint32_t stage = k % kStages, use = k / kStages;
-            const size_t row0 = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * kRows;
-            const size_t r = row0 + row;
-            const uint32_t rid = (uint32_t)__ldg(a.ray_ids + r);
-            // while the first layer's MMA runs: this row of the gathered features -> enc (the backward pass needs it),
-            // then release the operand tile to the gather warps
-            mbar_wait(bar_xfull + 8 * stage, use & 1u);
-            {
-                const uint32_t s_x = s_x0 + stage * kTileBytes;
-                uint4 *dst = reinterpret_cast<uint4 *>(a.enc + r * fs.enc_dim);
-                for (uint32_t c = 0; c < fs.enc_dim / 8; ++c) dst[c] = lds128(tile_chunk_addr(s_x, row, c));
-            }
-            mbar_arrive(bar_xempty + 8 * stage);
-            // this row's 256 B of the per-ray head bias, needed four layers from now: pull the lines into L1
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid * kHid));
-            asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid * kHid + 32));
+        const uint32_t wq = warp & 3u;                     // TMEM lane quadrant of this warp = rows 32 wq .. 32 wq + 31
+        const uint32_t row = wq * 32u + lane;
+        const uint32_t lane_sel = (wq * 32u) << 16;
+        uint32_t par[kSlotsPerGroup] = {};
+        size_t row0[kSlotsPerGroup] = {};
+        uint32_t rid[kSlotsPerGroup] = {};
 
-            // ---------------- density MLP ----------------
-            for (uint32_t layer = 0; layer <= fs.n_hid_s; ++layer) {
-                mbar_wait(done, par);
-                par ^= 1;
-                fence_after_sync();
-                uint4 pk[8];
-                row_relu_pack(d_hid, nullptr, pk);
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
-                fence_proxy_async();
-                fence_before_sync();
-                mbar_arrive(ready);
-                uint4 *dst = reinterpret_cast<uint4 *>(a.fb_s + ((size_t)layer * a.B + r) * kHid);   // while the tensor core works
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) dst[c] = pk[c];
+        // warp-local coalesced copy of this warp's 32 rows of a swizzled tile to global memory (row pitch `pitch_h`
+        // halves, `cpr` 16-byte chunks per row): every instruction writes 512 contiguous bytes
+        auto copy_rows_out = [&](uint32_t tile, __half *dst_row0, uint32_t cpr) {
+            for (uint32_t q = lane; q < 32 * cpr; q += 32) {
+                const uint32_t rr = wq * 32u + q / cpr, c = q % cpr;
+                *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * cpr + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
             }
-            // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand tile
-            mbar_wait(done, par);
-            par ^= 1;
-            fence_after_sync();
-            {
-                uint32_t v[16];
-                tmem_ld16(d_out, v);
-                tmem_ld_wait();
-                __half hv[16];
-#pragma unroll
-                for (uint32_t j = 0; j < 16; ++j) hv[j] = __float2half_rn(__uint_as_float(v[j]));
-                const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
-                uint4 *dst = reinterpret_cast<uint4 *>(a.sig_out + r * kOut);
-                dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
-                dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-                a.sigma[r] = __expf(__half2float(hv[0])) * a.density_scale;    // activation.py:6-20 (forward)
-                for (uint32_t c = 0; c < 2 * fs.ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
-#pragma unroll
-                for (uint32_t j = 1; j < 16; ++j) sts16h(elem_addr(s_h, row, fs.geo_off + j - 1), __half_as_ushort(hv[j]));
-            }
+        };
+        auto publish = [&](uint32_t bar) {                  // this warp's rows of an operand tile are in place
             fence_proxy_async();
             fence_before_sync();
-            mbar_arrive(ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
 
-            // ---------------- LiDAR head ----------------
-            const float4 *bias = reinterpret_cast<const float4 *>(a.ray_bias + (size_t)rid * kHid);
-            for (uint32_t layer = 0; layer <= fs.n_hid_h; ++layer) {
-                mbar_wait(done, par);
-                par ^= 1;
-                fence_after_sync();
-                uint4 pk[8];
-                row_relu_pack(d_hid, layer == 0 ? bias : nullptr, pk);
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
-                fence_proxy_async();
-                fence_before_sync();
-                mbar_arrive(ready);
-                uint4 *dst = reinterpret_cast<uint4 *>(a.fb_h + ((size_t)layer * a.B + r) * kHid);
-#pragma unroll
-                for (uint32_t c = 0; c < 8; ++c) dst[c] = pk[c];
+        for (uint32_t q = 0; q < kSlotsPerGroup; ++q)       // tensor memory of the group's slots is free
+            if (g * kSlotsPerGroup + q < n_my && lane == 0) mbar_arrive(bar_ready + 8 * (g * kSlotsPerGroup + q));
+
+        for (uint32_t k0 = g * kSlotsPerGroup; k0 < n_my; k0 += kSlots) {
+            const uint32_t nt = min(kSlotsPerGroup, n_my - k0);
+            // ---- per tile: gathered features -> enc (the backward pass needs them), release the operand tile ----
+            for (uint32_t t = 0; t < nt; ++t) {
+                const uint32_t k = k0 + t, stage = k % kStages, use = k / kStages;
+                row0[t] = ((size_t)blockIdx.x + (size_t)k * gridDim.x) * kRows;
+                rid[t] = (uint32_t)__ldg(a.ray_ids + row0[t] + row);
+                mbar_wait(bar_xfull + 8 * stage, use & 1u);
+                if (!(a.dbg & 2u)) copy_rows_out(s_x0 + stage * kTileBytes, a.enc + row0[t] * fs.enc_dim, fs.enc_dim / 8);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_xempty + 8 * stage);
+                // this row's 256 B of the per-ray head bias, needed four layers from now: pull the lines into L1
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid[t] * kHid));
+                asm volatile("prefetch.global.L1 [%0];" ::"l"(a.ray_bias + (size_t)rid[t] * kHid + 32));
             }
-            // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
-            mbar_wait(done, par);
-            par ^= 1;
-            fence_after_sync();
-            {
-                uint32_t v[16];
-                tmem_ld16(d_out, v);
-                tmem_ld_wait();
-                const float x0 = __half2float(__float2half_rn(__uint_as_float(v[0])));
-                const float x1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
-                reinterpret_cast<float2 *>(a.rgb)[r] = make_float2(1.f / (1.f + __expf(-x0)), 1.f / (1.f + __expf(-x1)));
+            // ---- the network, phase by phase, the group's tiles in turn (one tile's MMA runs under the other's epilogue) ----
+            for (uint32_t ph = 0; ph < n_steps; ++ph) {
+                for (uint32_t t = 0; t < nt; ++t) {
+                    const uint32_t slot = g * kSlotsPerGroup + t;
+                    const uint32_t d_hid = tmem + slot * kTmemColsPerSlot + lane_sel, d_out = d_hid + 64;
+                    const uint32_t s_h = s_h0 + slot * kTileBytes;
+                    const uint32_t ready = bar_ready + 8 * slot, done = bar_done + 8 * slot;
+                    const size_t r = row0[t] + row;
+                    mbar_wait(done, par[t]);
+                    par[t] ^= 1;
+                    fence_after_sync();
+                    const bool sigma_layer = ph <= fs.n_hid_s;
+                    const bool head_layer = ph >= fs.n_hid_s + 2 && ph <= fs.n_hid_s + 2 + fs.n_hid_h;
+                    if (sigma_layer || head_layer) {
+                        // hidden layer: accumulator row -> (+per-ray bias) -> ReLU -> fp16 -> operand tile of the next layer
+                        const uint32_t layer = sigma_layer ? ph : ph - (fs.n_hid_s + 2);
+                        const float4 *bias = (head_layer && layer == 0)
+                                                 ? reinterpret_cast<const float4 *>(a.ray_bias + (size_t)rid[t] * kHid) : nullptr;
+                        __syncwarp();                        // the previous layer's copy-out reads of this warp's rows are done
+                        if (!(a.dbg & 4u)) {
+                            uint4 pk[8];
+                            row_relu_pack(d_hid, bias, pk);
+#pragma unroll
+                            for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
+                        }
+                        publish(ready);
+                        if (!(a.dbg & 6u)) {                 // saved activations leave coalesced while the tensor core works
+                            __half *fb = sigma_layer ? a.fb_s : a.fb_h;
+                            copy_rows_out(s_h, fb + ((size_t)layer * a.B + row0[t]) * kHid, 8);
+                        }
+                    } else if (ph == fs.n_hid_s + 1) {
+                        // density output: sig_out (fp16, kept for backward), sigma = exp(h0) * scale, geo -> head operand
+                        uint32_t v[16];
+                        tmem_ld16(d_out, v);
+                        tmem_ld_wait();
+                        __half hv[16];
+#pragma unroll
+                        for (uint32_t j = 0; j < 16; ++j) hv[j] = __float2half_rn(__uint_as_float(v[j]));
+                        const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
+                        uint4 *dst = reinterpret_cast<uint4 *>(a.sig_out + r * kOut);
+                        dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
+                        dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
+                        a.sigma[r] = __expf(__half2float(hv[0])) * a.density_scale;    // activation.py:6-20 (forward)
+                        __syncwarp();                        // copy-out of the last hidden layer is done with these rows
+                        for (uint32_t c = 0; c < 2 * fs.ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
+#pragma unroll
+                        for (uint32_t j = 1; j < 16; ++j) sts16h(elem_addr(s_h, row, fs.geo_off + j - 1), __half_as_ushort(hv[j]));
+                        publish(ready);
+                    } else {
+                        // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
+                        uint32_t v[16];
+                        tmem_ld16(d_out, v);
+                        tmem_ld_wait();
+                        const float x0 = __half2float(__float2half_rn(__uint_as_float(v[0])));
+                        const float x1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
+                        reinterpret_cast<float2 *>(a.rgb)[r] = make_float2(1.f / (1.f + __expf(-x0)), 1.f / (1.f + __expf(-x1)));
+                        fence_before_sync();                 // this tile's TMEM reads are ordered before the next tile's MMAs
+                        __syncwarp();
+                        if (k0 + t + kSlots < n_my && lane == 0) mbar_arrive(ready);   // the slot's next tile may start
+                    }
+                }
             }
-            fence_before_sync();                            // this tile's TMEM reads are ordered before the next tile's MMAs
-            if (k + kGroups < n_my) mbar_arrive(ready);     // tensor memory drained: the group's next tile may start
         }
     } else {
         // ======================= MMA warp (converged; one elected lane issues) =======================
         mbar_wait_warp(bar_w, 0);                           // weight image landed (TMA transaction bytes complete)
-        uint32_t kk[kGroups], step[kGroups], par[kGroups];
+        uint32_t kk[kSlots], step[kSlots], par[kSlots];
         uint32_t left = 0;
 #pragma unroll
-        for (uint32_t g = 0; g < kGroups; ++g) {
-            kk[g] = g, step[g] = 0, par[g] = 0;
-            if (g < n_my) ++left;
+        for (uint32_t q = 0; q < kSlots; ++q) {
+            kk[q] = q, step[q] = 0, par[q] = 0;
+            if (q < n_my) ++left;
         }
         uint32_t spins = 0;
         while (left > 0) {
             bool progressed = false;
 #pragma unroll
-            for (uint32_t g = 0; g < kGroups; ++g) {
-                if (kk[g] >= n_my) continue;
-                if (!mbar_test_warp(bar_ready + 8 * g, par[g])) continue;
-                const uint32_t stage = kk[g] % kStages, use = kk[g] / kStages;
-                if (step[g] == 0 && !mbar_test_warp(bar_xfull + 8 * stage, use & 1u)) continue;
-                par[g] ^= 1;
+            for (uint32_t q = 0; q < kSlots; ++q) {
+                if (kk[q] >= n_my) continue;
+                if (!mbar_test_warp(bar_ready + 8 * q, par[q])) continue;
+                const uint32_t stage = kk[q] % kStages, use = kk[q] / kStages;
+                if (step[q] == 0 && !mbar_test_warp(bar_xfull + 8 * stage, use & 1u)) continue;
+                par[q] ^= 1;
                 fence_after_sync();
-                const uint32_t d_hid = tmem + g * kTmemColsPerGroup, d_out = d_hid + 64;
-                const uint32_t s_h = s_h0 + g * kTileBytes;
-                const uint32_t st = step[g];
+                const uint32_t d_hid = tmem + q * kTmemColsPerSlot, d_out = d_hid + 64;
+                const uint32_t s_h = s_h0 + q * kTileBytes;
+                const uint32_t st = step[q];
                 if (st == 0) {
                     issue_kmajor(d_hid, s_x0 + stage * kTileBytes, s_ws_in, ks_in, kIdescFwdHid, false);
                 } else if (st <= fs.n_hid_s) {
@@ -400,12 +492,12 @@ k_field_fused_fwd(const FusedArgs a) {
                 } else {
                     issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
                 }
-                mma_commit_elect(bar_done + 8 * g);
+                mma_commit_elect(bar_done + 8 * q);
                 if (st == 0) mma_commit_elect(bar_xempty + 8 * stage);     // the operand tile has been consumed
-                if (++step[g] == n_steps) {
-                    step[g] = 0;
-                    kk[g] += kGroups;
-                    if (kk[g] >= n_my) --left;
+                if (++step[q] == n_steps) {
+                    step[q] = 0;
+                    kk[q] += kSlots;
+                    if (kk[q] >= n_my) --left;
                 }
                 progressed = true;
             }
@@ -429,7 +521,8 @@ int make_fused_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_p
     fs->n_hid_s = sigma_layers - 1;
     fs->n_hid_h = head_layers - 1;
     fs->head_in = head_in_pad;
-    fs->nfreq = 3 + 6 * degree;
+    if (!dir_code_valid(degree)) return LNB_ERR_UNSUPPORTED;
+    fs->nfreq = dir_code_width(degree);
     if (fs->nfreq + 15 > head_in_pad) return LNB_ERR_INVALID_ARGUMENT;
     fs->geo_tile = fs->nfreq / 64;
     fs->geo_off = fs->nfreq % 64;
@@ -439,8 +532,8 @@ int make_fused_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_p
 }
 
 size_t fused_smem_bytes(const FusedShape &fs) {
-    return 1024 + weight_image_bytes(fs) + (size_t)(kStages + kGroups) * kTileBytes + 2 * kRows * 3 * 4 +
-           8 * (2 * kStages + 2 * kGroups + 1) + 16;
+    return 1024 + weight_image_bytes(fs) + (size_t)(kStages + kSlots) * kTileBytes + (size_t)kGatherWarps * kScratchPerWarp +
+           kCoordBufs * kRows * 3 * 4 + 8 * (2 * kStages + 2 * kSlots + 1) + 16;
 }
 
 int sm_count_fused() {
@@ -522,6 +615,11 @@ int lnb_field_fused_forward(const float *xyzs, const void *table, const int32_t 
     a.fb_h = static_cast<__half *>(fb_head);
     a.sigma = sigma;
     a.rgb = rgb;
+    {
+        static const uint32_t dbg = [] { const char *e = getenv("LNB_FUSED_DBG"); return e ? (uint32_t)atoi(e) : 0u; }();
+        a.dbg = dbg;
+        if (const char *e = getenv("LNB_FUSED_DBG_LIVE")) a.dbg = (uint32_t)atoi(e);      // re-read per call (diagnostics)
+    }
     const uint32_t tiles = M / kRows;
     const uint32_t cap = (uint32_t)sm_count_fused();
     k_field_fused_fwd<<<tiles < cap ? tiles : cap, kFusedThreads, smem, as_stream(stream)>>>(a);

@@ -28,6 +28,8 @@ class FieldConfig:
     sigma_layers: int = 2                # FFMLP num_layers
     head_layers: int = 2
     freq_degree: int = 12                # network.py:83
+    dir_encoding: str = "frequency"      # "frequency" (LiDAR head, network.py:83) | "sh" (spherical harmonics of degree
+    sh_degree: int = 4                   #   sh_degree, the direction encoder of network.py:64 / network_tcnn.py:74-80)
     geo_feat_dim: int = 15
     # loss (configs/kitti360_1908.txt:2-4)
     alpha_d: float = 1e3
@@ -59,6 +61,16 @@ class FieldConfig:
         return 1 + math.ceil(math.log2(self.bound))   # renderer.py:74
 
     @property
+    def dir_dim(self):
+        """Columns of the head input taken by the direction encoding."""
+        return self.sh_degree ** 2 if self.dir_encoding == "sh" else 3 + 6 * self.freq_degree
+
+    @property
+    def dir_code(self):
+        """The `degree` argument of the lnb_field_* entry points (LNB_DIR_SH(deg) = 0x100 | deg for SH)."""
+        return (0x100 | self.sh_degree) if self.dir_encoding == "sh" else self.freq_degree
+
+    @property
     def head_in_dim(self):
-        raw = 3 + 6 * self.freq_degree + self.geo_feat_dim        # 75 + 15 = 90
-        return (raw + 15) // 16 * 16                               # padded to 96 for the tensor cores
+        raw = self.dir_dim + self.geo_feat_dim                     # 75 + 15 = 90 (frequency 12) / 16 + 15 = 31 (SH 4)
+        return (raw + 15) // 16 * 16                               # padded to 96 / 32 for the tensor cores

@@ -152,11 +152,14 @@ class LidarFieldEngine:
 
         # fused field kernels: per-ray direction terms instead of a per-sample [M, 96] head input
         self.fused = bool(c.fused_field) and lib.lnb_field_supported(
-            u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+            u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
             u32(c.hidden_dim)) == 0
+        if c.dir_encoding == "sh" and not self.fused:
+            raise RuntimeError("dir_encoding='sh' is implemented by the fused field kernels only (fused_field=True, "
+                               "SH degree 4, 64-wide 2-layer MLPs)")
         # gather + MLPs as one persistent kernel: the MLP weights travel as a pre-laid-out shared-memory image (TMA)
         wbytes = int(lib.lnb_field_fused_weight_bytes(u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim),
-                                                      u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim)))
+                                                      u32(c.head_layers), u32(c.dir_code), u32(c.hidden_dim)))
         self.fused_gather = bool(c.fused_gather) and self.fused and wbytes > 0 and c.level_dim == 2
         self.wimage = torch.zeros(max(wbytes, 16), dtype=torch.uint8, device=dev) if self.fused_gather else None
         self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=torch.float16, device=dev)
@@ -267,13 +270,13 @@ class LidarFieldEngine:
             # per-ray direction terms depend only on rays_d and the head weights: a side branch next to the gather
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.freq_degree),
+                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.dir_code),
                                             u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
                     "ray_terms")
                 if self.fused_gather:
                     _ck(lib.lnb_field_pack_weights(p(self.w_sigma_h), p(self.w_head_h), u32(self.enc_dim),
                                                    u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
-                                                   u32(c.freq_degree), u32(c.hidden_dim), p(self.wimage), self._s()),
+                                                   u32(c.dir_code), u32(c.hidden_dim), p(self.wimage), self._s()),
                         "pack_weights")
         # every per-sample kernel below reads the produced count from `counter` ON THE DEVICE and only touches
         # round_up(count, 128) rows, so M can be sized generously (no dropped rays) at no cost
@@ -289,7 +292,7 @@ class LidarFieldEngine:
                                             u32(c.level_dim), f32(self.S), u32(c.base_resolution), f32(c.bound),
                                             p(self.wimage), p(self.ray_ids), p(self.ray_bias), u32(M),
                                             u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
-                                            u32(c.freq_degree), u32(c.hidden_dim), f32(c.density_scale), p(self.enc),
+                                            u32(c.dir_code), u32(c.hidden_dim), f32(c.density_scale), p(self.enc),
                                             p(self.fb_sigma), p(self.sig_out), p(self.sigma), p(self.fb_head),
                                             p(self.rgb), na, s), "field_fused_forward")
             return
@@ -301,7 +304,7 @@ class LidarFieldEngine:
             main.wait_stream(self._side)               # join: ray terms ready
             _ck(lib.lnb_field_forward(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
                                       p(self.ray_bias), u32(M), u32(self.enc_dim), u32(c.sigma_layers),
-                                      u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree), u32(c.hidden_dim),
+                                      u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code), u32(c.hidden_dim),
                                       f32(c.density_scale), p(self.fb_sigma), p(self.sig_out), p(self.sigma),
                                       p(self.fb_head), p(self.rgb), na, s), "field_forward")
         else:
@@ -376,7 +379,7 @@ class LidarFieldEngine:
             li = p(self.live_idx)
             _ck(lib.lnb_field_head_backward_rows(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                                  p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
-                                                 u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+                                                 u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
                                                  u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
                                                  p(self.g_head_w), li, nl, s), "field_head_backward_rows")
             _ck(lib.lnb_ffmlp_backward_accumulate_rows(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h),
@@ -394,7 +397,7 @@ class LidarFieldEngine:
         if self.fused:
             _ck(lib.lnb_field_head_backward(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                             p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
-                                            u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.freq_degree),
+                                            u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
                                             u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
                                             p(self.g_head_w), na, s), "field_head_backward")
         else:

@@ -55,7 +55,11 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
                                   level_scales)
     sig_out, fb_s = orc.ffmlp_forward(enc, w_sigma, params.enc_dim, 16, c.hidden_dim, c.sigma_layers)
     sigma = np.exp(sig_out[:, 0]).astype(np.float32) * np.float32(c.density_scale)
-    fenc = orc.freq_encode_forward(dirs, c.freq_degree)
+    # direction encoding of the head: frequency (network.py:83) or spherical harmonics (network.py:64), cfg.dir_encoding
+    if getattr(c, "dir_encoding", "frequency") == "sh":
+        fenc = orc.sh_encode_forward(dirs, c.sh_degree)
+    else:
+        fenc = orc.freq_encode_forward(dirs, c.freq_degree)
     head_in = np.zeros((M, c.head_in_dim), np.float32)
     head_in[:, :fenc.shape[1]] = fenc
     head_in[:, fenc.shape[1]:fenc.shape[1] + 15] = sig_out[:, 1:16]

@@ -69,9 +69,8 @@ def _small_net(seed=0):
     net = NeRFNetwork(encoding="hashgrid", desired_resolution=2048, log2_hashmap_size=15, bound=1,
                       min_near_lidar=1 / 92.7, density_thresh=10).to(DEV)
     g = torch.Generator().manual_seed(seed + 1)
-    net.encoder.embeddings.data.uniform_(-0.5, 0.5, generator=g)
-    net.sigma_net.weights.data.uniform_(-0.25, 0.25, generator=g)
-    net.lidar_color_net.weights.data.uniform_(-0.25, 0.25, generator=g)
+    for prm, b in ((net.encoder.embeddings, 0.5), (net.sigma_net.weights, 0.25), (net.lidar_color_net.weights, 0.25)):
+        prm.data.copy_(torch.empty(prm.shape).uniform_(-b, b, generator=g))
     net.grid_update_interval = 0
     return net
 
