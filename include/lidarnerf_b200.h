@@ -318,6 +318,31 @@ int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float
                               float loss_scale, float *weights_sum, float *depth, float *image, float *t0,
                               float *grad_sigmas, float *grad_rgbs, float *loss_out, int32_t *live_idx,
                               int32_t *n_live, lnb_stream_t stream);
+/* lnb_lidar_loss + the patch depth-gradient term of the KITTI-360 configurations (nerf/utils.py:748-876 with
+ * grad_loss = True, sobel_grad = False, depth_grad_loss = l1): rays arrive as patches [N / (px*py), px, py] of the range
+ * image (base_dataset.py:52-74, change_patch_size_lidar = [2, 8]) and the loss adds
+ *   alpha_grad * mean_{pairs (i,j),(i,j+1)} | |P - P'| mask - (G - G') mask |,  P = D m * inv_scale, G = d_gt m * inv_scale,
+ *   mask = m * [ |G - G'| < grad_clip ]  (the reference's 0.01), inv_scale = 1 / opt.scale.
+ * patch_x = patch_y = 1 or alpha_grad = 0 reduce it to lnb_lidar_loss. */
+int lnb_lidar_loss_ex(const float *weights_sum, const float *depth, const float *image, const float *gt,
+                      const float *t0, uint32_t N, float alpha_d, float alpha_r, float alpha_i, float loss_scale,
+                      uint32_t patch_x, uint32_t patch_y, float alpha_grad, float inv_scale, float grad_clip,
+                      float *g_weights_sum, float *g_depth, float *g_image, float *loss_out, lnb_stream_t stream);
+/* lnb_lidar_composite_step split at the loss, for losses that couple neighbouring rays (lnb_lidar_loss_ex):
+ *   lnb_lidar_composite_forward  -> weights_sum / depth / image / t0 of every ray;
+ *   lnb_lidar_composite_backward <- per-ray gradients g_weights_sum / g_depth / g_image (+ the forward results): sample
+ *   gradients for every marched row (zero behind the early stop) and the compact live-row list, as the one-pass kernel. */
+int lnb_lidar_composite_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                const float *gt, const float *nears, const float *noises, float dt_gamma,
+                                uint32_t max_steps, uint32_t C, uint32_t H, uint32_t M, uint32_t N, float T_thresh,
+                                float *weights_sum, float *depth, float *image, float *t0, lnb_stream_t stream);
+int lnb_lidar_composite_backward(const float *g_weights_sum, const float *g_depth, const float *g_image,
+                                 const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                 const float *gt, const float *nears, const float *noises, float dt_gamma,
+                                 uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
+                                 uint32_t N, float T_thresh, const float *weights_sum, const float *depth,
+                                 const float *image, float *grad_sigmas, float *grad_rgbs, int32_t *live_idx,
+                                 int32_t *n_live, lnb_stream_t stream);
 int lnb_field_head_out_grad(const float *g_rgb, const float *rgb, uint32_t M, void *g_head_out,
                             const int32_t *n_active, lnb_stream_t stream);
 int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const void *g_head_in, uint32_t M,

@@ -42,9 +42,7 @@ constexpr uint32_t kMmaWarpIdx = kEpiWarp0 + kGroups * 4;
 constexpr uint32_t kFusedThreads = (kMmaWarpIdx + 1) * 32;      // 800
 constexpr uint32_t kStages = 3;                        // operand tiles between the gather and the first MLP layer
 constexpr uint32_t kTmemColsPerSlot = 128;             // [0,64) hidden accumulator, [64,80) output accumulator
-constexpr uint32_t kRing = 4;                          // gather batches (32 samples x 8 corners) in flight per warp
-constexpr uint32_t kScratchPerWarp = kRing * 8 * 32 * 4;        // cp.async landing zone: [batch][corner][lane] x 4 B
-constexpr uint32_t kCoordBufs = 3;
+constexpr uint32_t kCoordBufs = 2;
 
 struct FusedShape {
     uint32_t enc_dim;        // L * C (multiple of 16, <= 64)
@@ -132,42 +130,38 @@ k_pack_field_weights(const __half *__restrict__ Ws, const __half *__restrict__ W
     put(off, Wh + wh_in_elems + (size_t)fs.n_hid_h * kHid * kHid, kOut, kHid, kHid);
 }
 
-// this thread's accumulator row (64 fp32 columns) -> (+bias) -> ReLU -> fp16: eight 16-byte chunks
-__device__ __forceinline__ void row_relu_pack(uint32_t d_row, const float4 *__restrict__ bias, uint4 (&pk)[8]) {
-    uint32_t v0[32], v1[32];
-    tmem_ld32(d_row, v0);
-    tmem_ld32(d_row + 32, v1);
-    tmem_ld_wait();
+// this thread's accumulator row (64 fp32 columns) -> (+bias) -> ReLU -> fp16 -> the row of the next layer's operand tile,
+// 32 columns at a time (keeps the epilogue at 72 registers: no setmaxnreg redistribution needed; the second tcgen05.ld's
+// latency is covered by the group's other tile)
+__device__ __forceinline__ void row_relu_to_tile(uint32_t d_row, const float4 *__restrict__ bias, uint32_t s_h, uint32_t row) {
 #pragma unroll
-    for (uint32_t c = 0; c < 8; ++c) {
-        float f[8];
+    for (uint32_t half = 0; half < 2; ++half) {
+        uint32_t v[32];
+        tmem_ld32(d_row + 32 * half, v);
+        tmem_ld_wait();
 #pragma unroll
-        for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(c < 4 ? v0[c * 8 + e] : v1[(c - 4) * 8 + e]);
-        if (bias) {
-            const float4 b0 = __ldg(bias + c * 2), b1 = __ldg(bias + c * 2 + 1);
-            f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
-            f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+        for (uint32_t c = 0; c < 4; ++c) {
+            float f[8];
+#pragma unroll
+            for (uint32_t e = 0; e < 8; ++e) f[e] = __uint_as_float(v[c * 8 + e]);
+            if (bias) {
+                const float4 b0 = __ldg(bias + half * 8 + c * 2), b1 = __ldg(bias + half * 8 + c * 2 + 1);
+                f[0] += b0.x, f[1] += b0.y, f[2] += b0.z, f[3] += b0.w;
+                f[4] += b1.x, f[5] += b1.y, f[6] += b1.z, f[7] += b1.w;
+            }
+            uint4 pk;
+            pk.x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
+            pk.y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
+            pk.z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
+            pk.w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
+            sts128(tile_chunk_addr(s_h, row, half * 4 + c), pk);
         }
-        pk[c].x = pack_half2(fmaxf(f[0], 0.f), fmaxf(f[1], 0.f));
-        pk[c].y = pack_half2(fmaxf(f[2], 0.f), fmaxf(f[3], 0.f));
-        pk[c].z = pack_half2(fmaxf(f[4], 0.f), fmaxf(f[5], 0.f));
-        pk[c].w = pack_half2(fmaxf(f[6], 0.f), fmaxf(f[7], 0.f));
     }
 }
 
-// four-byte asynchronous global -> shared copy (LDGSTS): a gathered table row lands in shared memory without occupying
-// a register while it is in flight
-__device__ __forceinline__ void cp_async4(uint32_t dst_smem, const void *src) {
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst_smem), "l"(src) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_pending(uint32_t n) {      // n = groups that may still be in flight
-    if (n == 0) asm volatile("cp.async.wait_group 0;" ::: "memory");
-    else if (n == 1) asm volatile("cp.async.wait_group 1;" ::: "memory");
-    else if (n == 2) asm volatile("cp.async.wait_group 2;" ::: "memory");
-    else asm volatile("cp.async.wait_group 3;" ::: "memory");
-}
-
+// (Measured and rejected: gathering with 4-byte cp.async into a per-warp shared-memory ring - no register per load in
+// flight, 24+ loads per lane outstanding - made the gather 2.5x SLOWER than plain LDG (257 vs ~100 us at 385 k samples):
+// LDGSTS of 4-byte elements is processed far below the LSU's gather rate.)
 __global__ void __launch_bounds__(kFusedThreads, 1)
 k_field_fused_fwd(const FusedArgs a) {
     extern __shared__ uint8_t smem_raw[];
@@ -183,8 +177,7 @@ k_field_fused_fwd(const FusedArgs a) {
     const uint32_t wbytes = weight_image_bytes(fs);
     const uint32_t s_x0 = sbase + wbytes;                          // kStages operand tiles written by the gather
     const uint32_t s_h0 = s_x0 + kStages * kTileBytes;             // one activation operand tile per slot
-    const uint32_t s_sc0 = s_h0 + kSlots * kTileBytes;             // gather landing zones, one per gather warp
-    const uint32_t s_in0 = s_sc0 + kGatherWarps * kScratchPerWarp; // kCoordBufs x [128][3] coordinates in [0,1]
+    const uint32_t s_in0 = s_h0 + kSlots * kTileBytes;             // kCoordBufs x [128][3] coordinates in [0,1]
     const uint32_t s_bar = s_in0 + kCoordBufs * kRows * 3 * 4;
     const uint32_t bar_xfull = s_bar, bar_xempty = bar_xfull + 8 * kStages, bar_ready = bar_xempty + 8 * kStages;
     const uint32_t bar_done = bar_ready + 8 * kSlots, bar_w = bar_done + 8 * kSlots, s_slot = bar_w + 8;
@@ -223,16 +216,12 @@ k_field_fused_fwd(const FusedArgs a) {
 
     if (warp < kGatherWarps) {
         // ======================= GATHER: warp <-> level =======================
-        // Register budget (setmaxnreg works per warpgroup = 4 consecutive warps): the CTA is launched with 72 registers x
-        // 800 threads; the gathered rows travel global -> shared by cp.async (no register per load in flight), so the 512
-        // gather threads can hand 24 registers each (72 -> 48) to the 256 epilogue threads (72 -> 120; a 64-column accumulator row per thread).
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 48;");
+        // (Registers: 25 warps -> 72 per thread for every role.  Redistributing with setmaxnreg was tried both ways -
+        // gather 48 / epilogue 120 with a 64-column epilogue, gather 80 / epilogue 56 - and bought nothing: the epilogue
+        // works on 32 accumulator columns at a time and the gather keeps 16 loads per lane in flight within 72.)
         const uint32_t tid = threadIdx.x;
         constexpr uint32_t D = 3, C = 2;
-        const uint32_t s_sc = s_sc0 + warp * kScratchPerWarp;
         const uint32_t nlv = warp < a.L ? (a.L - warp + kGatherWarps - 1) / kGatherWarps : 0;   // levels of this warp
-        const uint32_t per_tile = nlv * (kRows / 32);                                            // batches per tile
-        const uint32_t n_items = n_my * per_tile;
         // level-uniform quantities of the warp's first level, once per kernel
         LevelGeo g0 = {};
         LevelIndex<D> li0 = {};
@@ -245,70 +234,43 @@ k_field_fused_fwd(const FusedArgs a) {
                 const size_t tile = blockIdx.x + (size_t)k * gridDim.x;
                 float x = __ldg(a.xyz + tile * kRows * 3 + tid);
                 if (a.norm.x != 0.f) x = (x + a.norm.x) * a.norm.y;
-                s_in[(k % kCoordBufs) * kRows * 3 + tid] = x;
+                s_in[(k & 1u) * kRows * 3 + tid] = x;
             }
         };
-        // item -> (tile k, level, sample group); the cell of this lane's sample on that level
-        auto locate_item = [&](uint32_t item, uint32_t &k, uint32_t &level, uint32_t &sl, LevelGeo &g, LevelIndex<D> &li) -> Cell<D> {
-            k = item / per_tile;
-            const uint32_t rem = item - k * per_tile;
-            const uint32_t lv = rem >> 2, grp = rem & 3u;
-            level = warp + lv * kGatherWarps;
-            g = g0, li = li0;
-            if (lv != 0) {
-                g = level_geo(a.offsets, level, a.S, a.H);
-                li = level_index<D>(g, 0u, false);
-            }
-            sl = grp * 32 + lane;
-            const float *in = s_in + (k % kCoordBufs) * kRows * 3 + sl * D;
+        // the cell of this lane's sample `sl` of the tile whose coordinates are at `in`
+        auto locate_sample = [&](const float *in, uint32_t sl, const LevelGeo &g) -> Cell<D> {
             float v[D];
             bool inside = true;
 #pragma unroll
             for (uint32_t d = 0; d < D; ++d) {
-                v[d] = in[d];
+                v[d] = in[sl * D + d];
                 if (v[d] < 0 || v[d] > 1) inside = false;
             }
             return locate_unit<D>(v, inside, g, false, 0u);
         };
-        auto issue = [&](uint32_t item) {
-            uint32_t k, level, sl;
-            LevelGeo g;
-            LevelIndex<D> li;
-            const Cell<D> cell = locate_item(item, k, level, sl, g, li);
-            if (cell.inside && !(a.dbg & 1u)) {
-                const __half *__restrict__ tab = a.table + (size_t)g.table_offset * C;
-                const CornerRows<D> cr(li, cell.base);
-                const uint32_t dst = s_sc + ((item % kRing) * 8u * 32u + lane) * 4u;
+        // all 8 corner rows of a cell (raw half2 words): 8 independent loads in flight
+        auto load_corners = [&](const Cell<D> &cell, const LevelGeo &g, const LevelIndex<D> &li, const __half *tab,
+                                uint32_t (&raw)[8]) {
+            const CornerRows<D> cr(li, cell.base);
 #pragma unroll
-                for (uint32_t corner = 0; corner < 8; ++corner) {
-                    uint32_t row;
-                    if (li.generic) {
-                        uint32_t pp[D];
+            for (uint32_t corner = 0; corner < 8; ++corner) {
+                uint32_t row;
+                if (li.generic) {
+                    uint32_t pp[D];
 #pragma unroll
-                        for (uint32_t d = 0; d < D; ++d) pp[d] = cell.base[d] + ((corner >> d) & 1u);
-                        row = cell_row<D>(pp, 0u, false, g);
-                    } else {
-                        row = cr.row(corner);
-                    }
-                    cp_async4(dst + corner * 128u, tab + (size_t)row * C);
+                    for (uint32_t d = 0; d < D; ++d) pp[d] = cell.base[d] + ((corner >> d) & 1u);
+                    row = cell_row<D>(pp, 0u, false, g);
+                } else {
+                    row = cr.row(corner);
                 }
+                raw[corner] = (cell.inside && !(a.dbg & 1u)) ? __ldg(reinterpret_cast<const uint32_t *>(tab + (size_t)row * C)) : 0u;
             }
-            cp_async_commit();
         };
-        auto consume = [&](uint32_t item, uint32_t s_x) {
-            uint32_t k, level, sl;
-            LevelGeo g;
-            LevelIndex<D> li;
-            const Cell<D> cell = locate_item(item, k, level, sl, g, li);
-            // sum over the 8 corners, accumulated in fp16 in corner order exactly like interp_corners() / the reference
-            // (gridencoder.cu:173-199)
-            __half res[C];
-            res[0] = res[1] = __float2half_rn(0.f);
+        // sum over the 8 corners, accumulated in fp16 in corner order exactly like interp_corners() / the reference
+        // (gridencoder.cu:173-199); 0 outside the unit cube
+        auto blend = [&](const Cell<D> &cell, const uint32_t (&raw)[8]) -> uint32_t {
+            __half r0 = __float2half_rn(0.f), r1 = r0;
             if (cell.inside && !(a.dbg & 1u)) {
-                const uint32_t src = s_sc + ((item % kRing) * 8u * 32u + lane) * 4u;
-                uint32_t raw[8];
-#pragma unroll
-                for (uint32_t corner = 0; corner < 8; ++corner) raw[corner] = lds32(src + corner * 128u);
 #pragma unroll
                 for (uint32_t corner = 0; corner < 8; ++corner) {
                     float w = 1;
@@ -318,31 +280,42 @@ k_field_fused_fwd(const FusedArgs a) {
                         else w *= cell.frac[d];
                     }
                     const __half2 hv = *reinterpret_cast<const __half2 *>(&raw[corner]);
-                    res[0] = __float2half_rn(__half2float(res[0]) + w * __low2float(hv));
-                    res[1] = __float2half_rn(__half2float(res[1]) + w * __high2float(hv));
+                    r0 = __float2half_rn(__half2float(r0) + w * __low2float(hv));
+                    r1 = __float2half_rn(__half2float(r1) + w * __high2float(hv));
                 }
             }
-            sts32(elem_addr(s_x, sl, level * C), (uint32_t)__half_as_ushort(res[0]) | ((uint32_t)__half_as_ushort(res[1]) << 16));
+            return (uint32_t)__half_as_ushort(r0) | ((uint32_t)__half_as_ushort(r1) << 16);
         };
 
         stage_coords(0);
-        stage_coords(1);
-        uint32_t issued = 0;
         for (uint32_t k = 0; k < n_my; ++k) {
             const uint32_t stage = k % kStages, use = k / kStages;
-            // coordinates of tiles k and k + 1 are complete (staged one / two tiles ago); every warp has finished tile
-            // k - 1, whose coordinate buffer now takes tile k + 2
-            named_bar(1, kGatherThreads);
-            stage_coords(k + 2);
-            if (k == 0)
-                for (; issued < min(n_items, kRing - 1); ++issued) issue(issued);
+            named_bar(1, kGatherThreads);                   // coordinates of tile k complete; everybody is done with tile k - 1
+            stage_coords(k + 1);
             if (use > 0) mbar_wait(bar_xempty + 8 * stage, (use - 1) & 1u);
             const uint32_t s_x = s_x0 + stage * kTileBytes;
-            for (uint32_t j = 0; j < per_tile; ++j) {
-                const uint32_t item = k * per_tile + j;
-                if (issued < n_items) issue(issued++);       // keep kRing - 1 batches ahead of the one consumed next
-                cp_async_wait_pending(issued - item - 1);
-                consume(item, s_x);
+            const float *in = s_in + (k & 1u) * kRows * 3;
+            for (uint32_t lv = 0; lv < nlv; ++lv) {
+                const uint32_t level = warp + lv * kGatherWarps;
+                LevelGeo g = g0;
+                LevelIndex<D> li = li0;
+                if (lv != 0) {
+                    g = level_geo(a.offsets, level, a.S, a.H);
+                    li = level_index<D>(g, 0u, false);
+                }
+                const __half *__restrict__ tab = a.table + (size_t)g.table_offset * C;
+                // two sample groups at a time: 16 gathers in flight per lane (the 16 gather warps have to cover the
+                // L2 latency that 48 warps cover in the stand-alone encoder kernel)
+#pragma unroll
+                for (uint32_t pair = 0; pair < kRows / 64; ++pair) {
+                    const uint32_t sl_a = pair * 64 + lane, sl_b = sl_a + 32;
+                    const Cell<D> ca = locate_sample(in, sl_a, g), cb = locate_sample(in, sl_b, g);
+                    uint32_t ra[8], rb[8];
+                    load_corners(ca, g, li, tab, ra);
+                    load_corners(cb, g, li, tab, rb);
+                    sts32(elem_addr(s_x, sl_a, level * C), blend(ca, ra));
+                    sts32(elem_addr(s_x, sl_b, level * C), blend(cb, rb));
+                }
             }
             fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core
             __syncwarp();
@@ -350,7 +323,6 @@ k_field_fused_fwd(const FusedArgs a) {
         }
     } else if (warp < kMmaWarpIdx) {
         // ======================= EPILOGUE groups: thread = tile row, two tiles in flight per group =======================
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 120;");
         const uint32_t g = (warp - kEpiWarp0) >> 2;
         const uint32_t wq = warp & 3u;                     // TMEM lane quadrant of this warp = rows 32 wq .. 32 wq + 31
         const uint32_t row = wq * 32u + lane;
@@ -362,6 +334,14 @@ k_field_fused_fwd(const FusedArgs a) {
         // warp-local coalesced copy of this warp's 32 rows of a swizzled tile to global memory (row pitch `pitch_h`
         // halves, `cpr` 16-byte chunks per row): every instruction writes 512 contiguous bytes
         auto copy_rows_out = [&](uint32_t tile, __half *dst_row0, uint32_t cpr) {
+            if (cpr == 8) {                                  // 64-wide rows (saved activations): no division, 8 copies
+#pragma unroll
+                for (uint32_t j = 0; j < 8; ++j) {
+                    const uint32_t q = lane + 32 * j, rr = wq * 32u + (q >> 3), c = q & 7u;
+                    *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * 8 + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
+                }
+                return;
+            }
             for (uint32_t q = lane; q < 32 * cpr; q += 32) {
                 const uint32_t rr = wq * 32u + q / cpr, c = q % cpr;
                 *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * cpr + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
@@ -411,12 +391,7 @@ k_field_fused_fwd(const FusedArgs a) {
                         const float4 *bias = (head_layer && layer == 0)
                                                  ? reinterpret_cast<const float4 *>(a.ray_bias + (size_t)rid[t] * kHid) : nullptr;
                         __syncwarp();                        // the previous layer's copy-out reads of this warp's rows are done
-                        if (!(a.dbg & 4u)) {
-                            uint4 pk[8];
-                            row_relu_pack(d_hid, bias, pk);
-#pragma unroll
-                            for (uint32_t c = 0; c < 8; ++c) sts128(tile_chunk_addr(s_h, row, c), pk[c]);
-                        }
+                        if (!(a.dbg & 4u)) row_relu_to_tile(d_hid, bias, s_h, row);
                         publish(ready);
                         if (!(a.dbg & 6u)) {                 // saved activations leave coalesced while the tensor core works
                             __half *fb = sigma_layer ? a.fb_s : a.fb_h;
@@ -466,11 +441,17 @@ k_field_fused_fwd(const FusedArgs a) {
             if (q < n_my) ++left;
         }
         uint32_t spins = 0;
+        uint32_t next_x = 0;          // CTA-local index of the next tile whose first layer may be issued
         while (left > 0) {
             bool progressed = false;
 #pragma unroll
             for (uint32_t q = 0; q < kSlots; ++q) {
                 if (kk[q] >= n_my) continue;
+                // The operand ring is consumed strictly in tile order.  (A parity test is only meaningful for the NEXT
+                // completion of a barrier: asking for use u of a stage before use u - 1 has completed succeeds at once -
+                // four slots over three stages would otherwise start tile 3 on the stage tile 0 is still being gathered
+                // into.)
+                if (step[q] == 0 && kk[q] != next_x) continue;
                 if (!mbar_test_warp(bar_ready + 8 * q, par[q])) continue;
                 const uint32_t stage = kk[q] % kStages, use = kk[q] / kStages;
                 if (step[q] == 0 && !mbar_test_warp(bar_xfull + 8 * stage, use & 1u)) continue;
@@ -493,7 +474,10 @@ k_field_fused_fwd(const FusedArgs a) {
                     issue_kmajor(d_out, s_h, s_wh_out, 4, kIdescFwdOut, false);
                 }
                 mma_commit_elect(bar_done + 8 * q);
-                if (st == 0) mma_commit_elect(bar_xempty + 8 * stage);     // the operand tile has been consumed
+                if (st == 0) {
+                    mma_commit_elect(bar_xempty + 8 * stage);              // the operand tile has been consumed
+                    ++next_x;
+                }
                 if (++step[q] == n_steps) {
                     step[q] = 0;
                     kk[q] += kSlots;
@@ -532,8 +516,8 @@ int make_fused_shape(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_p
 }
 
 size_t fused_smem_bytes(const FusedShape &fs) {
-    return 1024 + weight_image_bytes(fs) + (size_t)(kStages + kSlots) * kTileBytes + (size_t)kGatherWarps * kScratchPerWarp +
-           kCoordBufs * kRows * 3 * 4 + 8 * (2 * kStages + 2 * kSlots + 1) + 16;
+    return 1024 + weight_image_bytes(fs) + (size_t)(kStages + kSlots) * kTileBytes + kCoordBufs * kRows * 3 * 4 +
+           8 * (2 * kStages + 2 * kSlots + 1) + 16;
 }
 
 int sm_count_fused() {

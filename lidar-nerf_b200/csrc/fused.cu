@@ -125,6 +125,75 @@ k_lidar_loss(const float *__restrict__ ws, const float *__restrict__ depth, cons
     if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss_out, l);
 }
 
+// The same loss plus the patch depth-gradient term of the KITTI-360 configurations (`grad_loss = True`,
+// `change_patch_size_lidar = [2, 8]`; nerf/utils.py:748-876, non-sobel branch, depth_grad_loss = l1).  Rays arrive as
+// patches [np, px, py] (base_dataset.py:52-74: px rows x py columns of the range image); with P = D m / scale and
+// G = d_gt m / scale (metres) the reference adds
+//     alpha_grad * mean_{patch, i, j < py-1} | |P_ij - P_i,j+1| mask - (G_ij - G_i,j+1) mask |,
+//     mask = m_ij * [ |G_ij - G_i,j+1| < grad_clip ]                                           (:846-866)
+// - the horizontal (x) differences only (the y differences are computed at :795-800 but enter no enabled term), the
+// prediction's difference in ABSOLUTE value against the SIGNED ground-truth difference, exactly as written there.
+// Thread n owns ray n and evaluates the (at most two) pairs it belongs to, so no atomics on the gradients.
+__device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
+
+__global__ void __launch_bounds__(kThreads)
+k_lidar_loss_patch(const float *__restrict__ ws, const float *__restrict__ depth, const float *__restrict__ image,
+                   const float *__restrict__ gt, const float *__restrict__ t0, uint32_t N, float a_d, float a_r,
+                   float a_i, float loss_scale, uint32_t px, uint32_t py, float a_grad, float inv_scale, float clip,
+                   float *__restrict__ g_ws, float *__restrict__ g_depth, float *__restrict__ g_image,
+                   float *__restrict__ loss_out) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    float l = 0.f;
+    if (n < N) {
+        const float m = gt[n * 3], gi = gt[n * 3 + 1] * m, gd = gt[n * 3 + 2] * m;
+        const float start = t0 ? t0[n] : 0.f;
+        const float D = depth[n] + start * ws[n];
+        const float e_d = D * m - gd;
+        const float e_r = image[n * 2] - m;
+        const float e_i = image[n * 2 + 1] * m - gi;
+        const float inv_n = 1.f / (float)N;
+        l = (a_d * fabsf(e_d) + a_r * e_r * e_r + a_i * e_i * e_i) * inv_n;
+        const float s = loss_scale * inv_n;
+        float gD = a_d * m * sgn(e_d) * s;
+        // ---- patch term ----
+        const uint32_t n_patch = N / (px * py);
+        if (py > 1 && n < n_patch * px * py) {
+            const float inv_pairs = 1.f / (float)(n_patch * px * (py - 1));
+            const uint32_t j = n % py;
+            const float P = D * m * inv_scale, G = gd * inv_scale;
+            auto other = [&](uint32_t q, float &Pq, float &Gq, float &mq) {
+                mq = gt[q * 3];
+                const float sq = t0 ? t0[q] : 0.f;
+                Pq = (depth[q] + sq * ws[q]) * mq * inv_scale;
+                Gq = gt[q * 3 + 2] * mq * inv_scale;
+            };
+            if (j + 1 < py) {              // pair (n, n + 1): this ray is the left element, the mask is its own
+                float P1, G1, m1;
+                other(n + 1, P1, G1, m1);
+                const float dg = G - G1, dp = fabsf(P - P1);
+                const float msk = m * (fabsf(dg) < clip ? 1.f : 0.f);
+                const float e = dp * msk - dg * msk;
+                l += a_grad * fabsf(e) * inv_pairs;
+                gD += a_grad * inv_pairs * loss_scale * sgn(e) * msk * sgn(P - P1) * m * inv_scale;
+            }
+            if (j > 0) {                   // pair (n - 1, n): right element, the mask belongs to the left ray
+                float P0, G0, m0;
+                other(n - 1, P0, G0, m0);
+                const float dg = G0 - G, dp = fabsf(P0 - P);
+                const float msk = m0 * (fabsf(dg) < clip ? 1.f : 0.f);
+                const float e = dp * msk - dg * msk;
+                gD -= a_grad * inv_pairs * loss_scale * sgn(e) * msk * sgn(P0 - P) * m * inv_scale;
+            }
+        }
+        g_depth[n] = gD;
+        g_ws[n] = gD * start;
+        g_image[n * 2] = 2.f * a_r * e_r * s;
+        g_image[n * 2 + 1] = 2.f * a_i * e_i * m * s;
+    }
+    l = warp_sum(l);
+    if ((threadIdx.x & 31) == 0 && l != 0.f) atomicAdd(loss_out, l);
+}
+
 // d loss / d head_out = [ g_rgb * s (1 - s), 0 ... 0 ]  (fp16 row of 16)
 __global__ void __launch_bounds__(kThreads)
 k_head_out_grad(const float *__restrict__ g_rgb, const float *__restrict__ rgb, uint32_t M,
@@ -234,6 +303,22 @@ int lnb_lidar_loss(const float *weights_sum, const float *depth, const float *im
     k_lidar_loss<<<nblk(N), kThreads, 0, as_stream(stream)>>>(weights_sum, depth, image, gt, t0, N, alpha_d, alpha_r,
                                                              alpha_i, loss_scale, g_weights_sum, g_depth, g_image,
                                                              loss_out);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_lidar_loss_ex(const float *weights_sum, const float *depth, const float *image, const float *gt,
+                      const float *t0, uint32_t N, float alpha_d, float alpha_r, float alpha_i, float loss_scale,
+                      uint32_t patch_x, uint32_t patch_y, float alpha_grad, float inv_scale, float grad_clip,
+                      float *g_weights_sum, float *g_depth, float *g_image, float *loss_out, lnb_stream_t stream) {
+    if (!weights_sum || !depth || !image || !gt || !g_weights_sum || !g_depth || !g_image || !loss_out)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (patch_x == 0 || patch_y == 0 || patch_x * patch_y > N + (N == 0)) return LNB_ERR_INVALID_ARGUMENT;
+    if (N == 0) return LNB_OK;
+    k_lidar_loss_patch<<<nblk(N), kThreads, 0, as_stream(stream)>>>(weights_sum, depth, image, gt, t0, N, alpha_d, alpha_r,
+                                                                   alpha_i, loss_scale, patch_x, patch_y, alpha_grad,
+                                                                   inv_scale, grad_clip, g_weights_sum, g_depth, g_image,
+                                                                   loss_out);
     count_launch();
     return launch_status();
 }

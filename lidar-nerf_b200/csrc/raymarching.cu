@@ -651,6 +651,13 @@ k_composite_train_bwd(const float *__restrict__ g_ws, const float *__restrict__ 
 // their gradients never make a round trip through global memory, and every sample of the ray gets a gradient
 // written - zero after the early stop - which removes the zero-fill of the two gradient buffers from the step.
 // Same arithmetic, in the same order, as k_composite_train_fwd + k_lidar_loss + k_composite_train_bwd<2, true>.
+//
+// kMode 0: all of it in one pass (per-ray losses only).  A loss that couples NEIGHBOURING rays (the patch depth-gradient
+// term, nerf/utils.py:748-876) needs every ray's depth before any gradient exists, so the step is then split at the loss:
+// kMode 1 = forward only (weights_sum / depth / image / t0 out), then lnb_lidar_loss_ex, then kMode 2 = backward with the
+// per-ray gradients read from ext_g_ws / ext_g_depth / ext_g_image (forward results re-read from the output arrays),
+// still producing the zero-filled sample gradients and the compact live-row list.
+template <int kMode>
 __global__ void __launch_bounds__(kThreads)
 k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict__ rgbs,
                        const float *__restrict__ deltas, const int32_t *__restrict__ rays,
@@ -660,12 +667,14 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
                        float a_r, float a_i, float loss_scale, float *__restrict__ weights_sum,
                        float *__restrict__ depth, float *__restrict__ image, float *__restrict__ t0_out,
                        float *__restrict__ grad_sigmas, float *__restrict__ grad_rgbs,
-                       float *__restrict__ loss_out, int32_t *__restrict__ live_idx, int32_t *__restrict__ n_live) {
+                       float *__restrict__ loss_out, int32_t *__restrict__ live_idx, int32_t *__restrict__ n_live,
+                       const float *__restrict__ ext_g_ws, const float *__restrict__ ext_g_depth,
+                       const float *__restrict__ ext_g_image) {
     constexpr int NCH = 2;
     const uint32_t n = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     if (n >= N) return;
     const unsigned lane = lane_id();
-    if (n == 0 && counter) {
+    if (kMode != 1 && n == 0 && counter) {
         // rows between the produced count and the next 128-row tile boundary are processed by the per-sample
         // kernels but belong to no ray: their gradients are zero
         const uint32_t cnt = (uint32_t)max(*counter, 0);
@@ -684,7 +693,13 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
     // ---------------- forward ----------------
     float c_final[NCH] = {0.f, 0.f};
     float ws_final = 0.f, d_final = 0.f;
-    if (marched) {
+    if (kMode == 2) {
+        ws_final = weights_sum[index];
+        d_final = depth[index];
+        const float2 im = reinterpret_cast<const float2 *>(image)[index];
+        c_final[0] = im.x, c_final[1] = im.y;
+    }
+    if (kMode != 2 && marched) {
         float T_in = 1.0f, t_in = 0.f;
         for (uint32_t base = 0; base < count; base += 32) {
             const uint32_t i = base + lane;
@@ -734,18 +749,26 @@ k_lidar_composite_step(const float *__restrict__ sigmas, const float *__restrict
     const float e_i = c_final[1] * m - gti;
     const float inv_n = 1.f / (float)N;
     const float sc = loss_scale * inv_n;
-    const float gd = a_d * m * (e_d > 0.f ? 1.f : (e_d < 0.f ? -1.f : 0.f)) * sc;
-    const float gw = gd * start;
-    const float gi[NCH] = {2.f * a_r * e_r * sc, 2.f * a_i * e_i * m * sc};
-    if (lane == 0) {
+    float gd = a_d * m * (e_d > 0.f ? 1.f : (e_d < 0.f ? -1.f : 0.f)) * sc;
+    float gw = gd * start;
+    float gi[NCH] = {2.f * a_r * e_r * sc, 2.f * a_i * e_i * m * sc};
+    if (kMode == 2) {
+        gd = ext_g_depth[index];
+        gw = ext_g_ws[index];
+        const float2 g2 = reinterpret_cast<const float2 *>(ext_g_image)[index];
+        gi[0] = g2.x, gi[1] = g2.y;
+    }
+    if (kMode != 2 && lane == 0) {
         weights_sum[index] = ws_final;
         depth[index] = d_final;
         reinterpret_cast<float2 *>(image)[index] = make_float2(c_final[0], c_final[1]);
         if (t0_out) t0_out[index] = start;
-        const float l = (a_d * fabsf(e_d) + a_r * e_r * e_r + a_i * e_i * e_i) * inv_n;
-        if (l != 0.f) atomicAdd(loss_out, l);
+        if (kMode == 0) {
+            const float l = (a_d * fabsf(e_d) + a_r * e_r * e_r + a_i * e_i * e_i) * inv_n;
+            if (l != 0.f) atomicAdd(loss_out, l);
+        }
     }
-    if (!marched) return;
+    if (kMode == 1 || !marched) return;
 
     // ---------------- backward ----------------
     float c_in[NCH] = {0.f, 0.f};
@@ -1066,10 +1089,51 @@ int lnb_lidar_composite_step(const float *sigmas, const float *rgbs, const float
     const float two_sqrt3 = 2 * 1.7320508075688772f;       // same expressions as make_const()
     const float dt_min = two_sqrt3 / max_steps;
     const float dt_max = two_sqrt3 * (1 << (C - 1)) / H;
-    k_lidar_composite_step<<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+    k_lidar_composite_step<0><<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
         sigmas, rgbs, deltas, rays, gt, nears, noises, dt_gamma, dt_min, dt_max, counter, M, N, T_thresh, alpha_d,
         alpha_r, alpha_i, loss_scale, weights_sum, depth, image, t0, grad_sigmas, grad_rgbs, loss_out, live_idx,
-        n_live);
+        n_live, nullptr, nullptr, nullptr);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_lidar_composite_forward(const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                const float *gt, const float *nears, const float *noises, float dt_gamma,
+                                uint32_t max_steps, uint32_t C, uint32_t H, uint32_t M, uint32_t N, float T_thresh,
+                                float *weights_sum, float *depth, float *image, float *t0, lnb_stream_t stream) {
+    LNB_REQUIRE(rays && gt && nears && noises && weights_sum && depth && image);
+    LNB_REQUIRE(M == 0 || (sigmas && rgbs && deltas));
+    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && max_steps >= 1);
+    if (N == 0) return LNB_OK;
+    const float two_sqrt3 = 2 * 1.7320508075688772f;
+    const float dt_min = two_sqrt3 / max_steps;
+    const float dt_max = two_sqrt3 * (1 << (C - 1)) / H;
+    k_lidar_composite_step<1><<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, gt, nears, noises, dt_gamma, dt_min, dt_max, nullptr, M, N, T_thresh, 0.f, 0.f, 0.f,
+        0.f, weights_sum, depth, image, t0, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_lidar_composite_backward(const float *g_weights_sum, const float *g_depth, const float *g_image,
+                                 const float *sigmas, const float *rgbs, const float *deltas, const int32_t *rays,
+                                 const float *gt, const float *nears, const float *noises, float dt_gamma,
+                                 uint32_t max_steps, uint32_t C, uint32_t H, const int32_t *counter, uint32_t M,
+                                 uint32_t N, float T_thresh, const float *weights_sum, const float *depth,
+                                 const float *image, float *grad_sigmas, float *grad_rgbs, int32_t *live_idx,
+                                 int32_t *n_live, lnb_stream_t stream) {
+    LNB_REQUIRE((live_idx == nullptr) == (n_live == nullptr));
+    LNB_REQUIRE(g_weights_sum && g_depth && g_image && rays && gt && nears && noises && weights_sum && depth && image);
+    LNB_REQUIRE(M == 0 || (sigmas && rgbs && deltas && grad_sigmas && grad_rgbs));
+    LNB_REQUIRE(C >= 1 && C <= 8 && H >= 1 && max_steps >= 1);
+    if (N == 0) return LNB_OK;
+    const float two_sqrt3 = 2 * 1.7320508075688772f;
+    const float dt_min = two_sqrt3 / max_steps;
+    const float dt_max = two_sqrt3 * (1 << (C - 1)) / H;
+    k_lidar_composite_step<2><<<blocks_for_threads((uint64_t)N * 32, kThreads), kThreads, 0, as_stream(stream)>>>(
+        sigmas, rgbs, deltas, rays, gt, nears, noises, dt_gamma, dt_min, dt_max, counter, M, N, T_thresh, 0.f, 0.f, 0.f,
+        0.f, const_cast<float *>(weights_sum), const_cast<float *>(depth), const_cast<float *>(image), nullptr,
+        grad_sigmas, grad_rgbs, nullptr, live_idx, n_live, g_weights_sum, g_depth, g_image);
     count_launch();
     return launch_status();
 }

@@ -35,6 +35,11 @@ class FieldConfig:
     alpha_d: float = 1e3
     alpha_r: float = 1.0
     alpha_i: float = 10.0
+    # patch depth-gradient loss (configs/kitti360_1908.txt:5-6,8: alpha_grad = 100, grad_loss = True, patches of 2 x 8
+    # pixels every other epoch; nerf/utils.py:748-876).  patch = (1, 1) or alpha_grad = 0: per-ray loss only.
+    patch_size: tuple = (1, 1)
+    alpha_grad: float = 0.0
+    grad_clip: float = 0.01              # nerf/utils.py:846-849
     # optimiser (main_lidarnerf.py:389-391, lr default 1e-2)
     lr: float = 1e-2
     beta1: float = 0.9
@@ -59,6 +64,10 @@ class FieldConfig:
     @property
     def cascade(self):
         return 1 + math.ceil(math.log2(self.bound))   # renderer.py:74
+
+    @property
+    def patch_loss(self):
+        return self.alpha_grad > 0 and self.patch_size[0] * self.patch_size[1] > 1
 
     @property
     def dir_dim(self):

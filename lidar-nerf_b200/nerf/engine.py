@@ -346,7 +346,25 @@ class LidarFieldEngine:
         na = p(self.counter)
         compact = self._compact()
         nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
-        if c.fused_composite:
+        if c.fused_composite and c.patch_loss:
+            # a loss that couples neighbouring rays: forward of every ray -> loss + per-ray gradients -> backward
+            _ck(lib.lnb_lidar_composite_forward(p(self.sigma), p(self.rgb), p(self.deltas), p(self.rays), p(self.gt),
+                                                p(self.nears), p(self.noises), f32(c.dt_gamma), u32(c.max_steps),
+                                                u32(c.cascade), u32(c.grid_size), u32(M), u32(N), f32(c.T_thresh),
+                                                p(self.ws), p(self.depth), p(self.image), p(self.t0), s),
+                "lidar_composite_forward")
+            _ck(lib.lnb_lidar_loss_ex(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N),
+                                      f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale),
+                                      u32(c.patch_size[0]), u32(c.patch_size[1]), f32(c.alpha_grad),
+                                      f32(1.0 / c.min_near_lidar), f32(c.grad_clip), p(self.g_ws), p(self.g_depth),
+                                      p(self.g_image), p(self.loss_acc), s), "lidar_loss_ex")
+            _ck(lib.lnb_lidar_composite_backward(p(self.g_ws), p(self.g_depth), p(self.g_image), p(self.sigma), p(self.rgb),
+                                                 p(self.deltas), p(self.rays), p(self.gt), p(self.nears), p(self.noises),
+                                                 f32(c.dt_gamma), u32(c.max_steps), u32(c.cascade), u32(c.grid_size), na,
+                                                 u32(M), u32(N), f32(c.T_thresh), p(self.ws), p(self.depth), p(self.image),
+                                                 p(self.g_sigma), p(self.g_rgb), p(self.live_idx) if compact else vp(0),
+                                                 nl if compact else vp(0), s), "lidar_composite_backward")
+        elif c.fused_composite:
             _ck(lib.lnb_lidar_composite_step(p(self.sigma), p(self.rgb), p(self.deltas), p(self.rays), p(self.gt),
                                              p(self.nears), p(self.noises), f32(c.dt_gamma), u32(c.max_steps),
                                              u32(c.cascade), u32(c.grid_size), na, u32(M), u32(N), f32(c.T_thresh),
@@ -356,9 +374,11 @@ class LidarFieldEngine:
                                              nl if compact else vp(0), s), "lidar_composite_step")
         else:
             self.composite_forward()
-            _ck(lib.lnb_lidar_loss(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N),
-                                   f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale), p(self.g_ws),
-                                   p(self.g_depth), p(self.g_image), p(self.loss_acc), s), "lidar_loss")
+            _ck(lib.lnb_lidar_loss_ex(p(self.ws), p(self.depth), p(self.image), p(self.gt), p(self.t0), u32(N),
+                                      f32(c.alpha_d), f32(c.alpha_r), f32(c.alpha_i), f32(c.loss_scale),
+                                      u32(c.patch_size[0]), u32(c.patch_size[1]), f32(c.alpha_grad if c.patch_loss else 0.0),
+                                      f32(1.0 / c.min_near_lidar), f32(c.grad_clip), p(self.g_ws), p(self.g_depth),
+                                      p(self.g_image), p(self.loss_acc), s), "lidar_loss")
             self.composite_backward()
 
     def _bwd_field(self):

@@ -14,8 +14,10 @@ def small_config(**over):
     return FieldConfig(**kw)
 
 
-def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2):
-    """One forward/backward (no Adam) on both sides.  Returns (engine, gpu_result, cpu_result)."""
+def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2, patch_smooth_gt=False):
+    """One forward/backward (no Adam) on both sides.  Returns (engine, gpu_result, cpu_result).
+    patch_smooth_gt: ground-truth depth varies by < 1 cm between the rays of a patch of cfg.patch_size (so that the
+    patch depth-gradient term of the loss is active on most pairs)."""
     from lidar_nerf_b200.nerf.engine import LidarFieldEngine
     cfg = cfg or small_config()
     rng = np.random.default_rng(seed)
@@ -26,6 +28,12 @@ def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2):
     rays_d = (d / np.linalg.norm(d, axis=1, keepdims=True)).astype(np.float32)
     gt = np.stack([(rng.random(n_rays) < 0.9).astype(np.float32), rng.uniform(0, 1, n_rays),
                    rng.uniform(0.05, 0.8, n_rays)], -1).astype(np.float32)
+    if patch_smooth_gt:
+        px, py = cfg.patch_size
+        n_patch = n_rays // (px * py)
+        base = np.repeat(rng.uniform(0.05, 0.8, n_patch), px * py)
+        wiggle = rng.uniform(-0.3, 0.3, n_patch * px * py) * 0.01 * cfg.min_near_lidar       # < 1 cm in metres
+        gt[:n_patch * px * py, 2] = (base + wiggle).astype(np.float32)
     # a clumpy occupancy grid
     bits = np.zeros(cfg.cascade * cfg.grid_size ** 3, bool)
     pos = 0

@@ -36,6 +36,41 @@ class FieldParams:
         return flat[:a].reshape(self.n_rows, self.cfg.level_dim), flat[a:b], flat[b:]
 
 
+def lidar_loss(D, image, gt, a_d, a_r, a_i, loss_scale=1.0, patch=(1, 1), a_grad=0.0, inv_scale=1.0, clip=0.01):
+    """LiDAR loss of Trainer.train_step (nerf/utils.py:707-734) and its gradient w.r.t. the rendered absolute depth D [N]
+    and image [N,2]; gt rows = (ray-drop mask, intensity, depth).  With `patch` = (px, py) > 1 and a_grad > 0 it includes
+    the patch depth-gradient term (:748-876, sobel_grad = False, depth_grad_loss = l1): the rays are patches
+    [N / (px py), px, py] and the HORIZONTAL differences of P = D m / scale are compared - in absolute value - with the
+    signed differences of G = d_gt m / scale where the ground truth is locally flat (|dG| < clip) and returned.
+    Returns (loss, g_D * loss_scale, g_image * loss_scale)."""
+    N = D.shape[0]
+    m = gt[:, 0]
+    gi, gd = gt[:, 1] * m, gt[:, 2] * m
+    e_d, e_r, e_i = D * m - gd, image[:, 0] - m, image[:, 1] * m - gi
+    loss = float(np.mean(a_d * np.abs(e_d) + a_r * e_r ** 2 + a_i * e_i ** 2))
+    s = np.float32(loss_scale / N)
+    gD = (a_d * m * np.sign(e_d) * s).astype(np.float32)
+    g_img = np.stack([2 * a_r * e_r * s, 2 * a_i * e_i * m * s], -1).astype(np.float32)
+    px, py = patch
+    if a_grad > 0 and px * py > 1 and py > 1:
+        n_patch = N // (px * py)
+        n = n_patch * px * py
+        P = (D[:n] * m[:n] * np.float32(inv_scale)).reshape(n_patch, px, py)
+        G = (gd[:n] * np.float32(inv_scale)).reshape(n_patch, px, py)
+        mm = m[:n].reshape(n_patch, px, py)
+        dps = P[:, :, :-1] - P[:, :, 1:]
+        dg = G[:, :, :-1] - G[:, :, 1:]
+        msk = mm[:, :, :-1] * (np.abs(dg) < clip)
+        e = np.abs(dps) * msk - dg * msk
+        loss += float(a_grad * np.mean(np.abs(e)))
+        contrib = (a_grad / e.size) * np.sign(e) * msk * np.sign(dps)
+        gP = np.zeros_like(P)
+        gP[:, :, :-1] += contrib
+        gP[:, :, 1:] -= contrib
+        gD[:n] += (gP.reshape(-1) * m[:n] * np.float32(inv_scale) * np.float32(loss_scale)).astype(np.float32)
+    return loss, gD, g_img
+
+
 def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, level_scales=None, apply_adam=True):
     """Returns dict(loss, grad (flat fp32, unscaled), counts, ws, depth, image, n_samples)."""
     c = params.cfg
@@ -68,16 +103,13 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
     rgb = (1.0 / (1.0 + np.exp(-head_out[:, :2]))).astype(np.float32)
     ws, depth, image = orc.composite_rays_train_forward(sigma, rgb, deltas, rays, c.T_thresh)
 
-    # loss (nerf/utils.py:726-734) with absolute depth = depth + t0 * ws
-    m = gt[:, 0]
-    gi, gd = gt[:, 1] * m, gt[:, 2] * m
+    # loss (nerf/utils.py:726-734, + the patch term of :748-876) with absolute depth = depth + t0 * ws
     D = depth + t0 * ws
-    e_d, e_r, e_i = D * m - gd, image[:, 0] - m, image[:, 1] * m - gi
-    loss = float(np.mean(c.alpha_d * np.abs(e_d) + c.alpha_r * e_r ** 2 + c.alpha_i * e_i ** 2))
-    s = np.float32(c.loss_scale / N)
-    gD = (c.alpha_d * m * np.sign(e_d) * s).astype(np.float32)
+    px, py = getattr(c, "patch_size", (1, 1))
+    a_grad = getattr(c, "alpha_grad", 0.0) if px * py > 1 else 0.0
+    loss, gD, g_img = lidar_loss(D, image, gt, c.alpha_d, c.alpha_r, c.alpha_i, c.loss_scale, (px, py), a_grad,
+                                 1.0 / c.min_near_lidar, getattr(c, "grad_clip", 0.01))
     g_ws = (gD * t0).astype(np.float32)
-    g_img = np.stack([2 * c.alpha_r * e_r * s, 2 * c.alpha_i * e_i * m * s], -1).astype(np.float32)
 
     g_sigma, g_rgb = orc.composite_rays_train_backward(g_ws, g_img, sigma, rgb, deltas, rays, ws, image, c.T_thresh, gD,
                                                        depth)

@@ -11,6 +11,9 @@ the resulting small fixtures are committed and pin the CPU oracle / host logic:
                          deterministic PDF up-sampling) with an analytic density/colour field
   ref_py_sample_pdf.npz  lidarnerf/nerf/renderer.py:10-46 sample_pdf(det=True)
   ref_py_convert.npz     lidarnerf/convert.py:99-160,194-235 lidar_to_pano_with_intensities / pano_to_lidar_with_intensities
+  ref_py_patch_loss.npz  lidarnerf/nerf/utils.py:697-876 Trainer.train_step: the LiDAR loss INCLUDING the patch depth-gradient
+                         term (grad_loss = True, patches of 2 x 8 rays) and its autograd gradient w.r.t. the rendered
+                         depth / image, on given render outputs
 
 Usage: python tests/golden/make_golden_cpu.py
 """
@@ -62,6 +65,59 @@ def make_convert():
     save("ref_py_convert.npz", points=pts, H=H, W=W, K=np.array(K, np.float32), pano=pano, intensities=inten,
          back=back, numpy_version=np.__version__)
 
+
+# ---- LiDAR loss with the patch depth-gradient term (lidarnerf/nerf/utils.py:697-876) -------------------------
+def make_patch_loss():
+    """Calls the reference's own Trainer.train_step on a stand-in `self` whose model returns given render outputs."""
+    import argparse
+    for name in ("imageio", "lpips", "mcubes", "tensorboardX", "torch_ema", "skimage", "skimage.metrics", "extern",
+                 "extern.chamfer3D", "extern.chamfer3D.dist_chamfer_3D", "extern.fscore"):
+        sys.modules.setdefault(name, types.ModuleType(name))
+    sys.modules["torch_ema"].ExponentialMovingAverage = object
+    sys.modules["skimage.metrics"].structural_similarity = None
+    sys.modules["extern.chamfer3D.dist_chamfer_3D"].chamfer_3DDist = object
+    sys.modules["extern.fscore"].fscore = None
+    from lidarnerf.nerf.utils import Trainer
+    r = np.random.default_rng(11)
+    px, py, n_patch = 2, 8, 24
+    N = n_patch * px * py
+    scale = 0.010784853507573345                       # configs/kitti360_1908.txt:11
+    # smooth ground-truth depth inside a patch (so that |dG| < 0.01 m happens) with a few jumps and dropped rays
+    base = r.uniform(5, 60, size=(n_patch, 1, 1))
+    slope = r.uniform(-0.004, 0.004, size=(n_patch, 1, 1)) * np.arange(py)[None, None, :]
+    jump = (r.random((n_patch, px, py)) < 0.15) * r.uniform(0.5, 3.0, size=(n_patch, px, py))
+    gt_depth_m = base + slope + jump + r.normal(scale=0.002, size=(n_patch, px, py))
+    mask = (r.random((n_patch, px, py)) > 0.12).astype(np.float32)
+    gt = np.stack([mask, r.uniform(0, 1, size=mask.shape) * mask, gt_depth_m * scale * mask], -1).reshape(N, 3).astype(np.float32)
+    depth = (gt_depth_m * scale + r.normal(scale=0.004 * scale * 20, size=gt_depth_m.shape)).reshape(N).astype(np.float32)
+    image = r.uniform(0.02, 0.98, size=(N, 2)).astype(np.float32)
+    depth_t = torch.tensor(depth, requires_grad=True)
+    image_t = torch.tensor(image, requires_grad=True)
+
+    class Model:
+        def render(self, ro, rd, **kw):
+            return {"depth_lidar": depth_t[None], "image_lidar": image_t[None]}
+    opt = argparse.Namespace(enable_lidar=True, patch_size=1, alpha_d=1e3, alpha_r=1.0, alpha_i=10.0, alpha_grad=100.0,
+                             patch_size_lidar=[px, py], scale=scale, sobel_grad=False, grad_norm_smooth=False,
+                             spatial_smooth=False, tv_loss=False, grad_loss=True, depth_grad_loss="l1")
+    crit = {"depth": torch.nn.L1Loss(reduction="none"), "raydrop": torch.nn.MSELoss(reduction="none"),
+            "intensity": torch.nn.MSELoss(reduction="none"), "grad": torch.nn.L1Loss(reduction="none")}
+    me = types.SimpleNamespace(opt=opt, model=Model(), criterion=crit, device=torch.device("cpu"))
+    data = {"rays_o_lidar": torch.zeros(1, N, 3), "rays_d_lidar": torch.zeros(1, N, 3), "images_lidar": torch.tensor(gt)[None]}
+    loss = Trainer.train_step(me, data)[-1]
+    loss.backward()
+    opt.grad_loss = False                               # the per-ray part alone, for reference
+    depth_t2, image_t2 = depth_t.detach().clone().requires_grad_(True), image_t.detach().clone().requires_grad_(True)
+    Model.render = lambda self, ro, rd, **kw: {"depth_lidar": depth_t2[None], "image_lidar": image_t2[None]}
+    loss0 = Trainer.train_step(me, data)[-1]
+    save("ref_py_patch_loss.npz", depth=depth, image=image, gt=gt, scale=scale, patch=np.array([px, py]), alpha_d=1e3,
+         alpha_r=1.0, alpha_i=10.0, alpha_grad=100.0, loss=float(loss), loss_without_grad_term=float(loss0),
+         g_depth=depth_t.grad.numpy(), g_image=image_t.grad.numpy())
+
+
+if sys.argv[1:] == ["patch_loss"]:   # `python tests/golden/make_golden_cpu.py patch_loss`: only this fixture
+    make_patch_loss()
+    sys.exit(0)
 
 make_convert()
 if sys.argv[1:] == ["convert"]:      # `python tests/golden/make_golden_cpu.py convert`: only this fixture
@@ -155,3 +211,5 @@ with torch.no_grad():
 save("ref_py_run.npz", rays_o=orig, rays_d=dirs, num_steps=48, upsample_steps=16, min_near_lidar=0.01,
      depth=out["depth_lidar"][0].numpy(), image=out["image_lidar"][0].numpy(),
      weights_sum=out["weights_sum_lidar"].numpy())
+
+make_patch_loss()
