@@ -27,6 +27,25 @@ WORKLOAD = ("KITTI-360-like synthetic 64x1024 pano x 8 frames, hashgrid L16 F2 T
             "fwd+bwd+Adam(13.7M params)+grid refresh/16 steps")
 RAYS = 4096
 
+# BASELINE.json configs this bench can run (`--config`; 2 = configs[1] is the headline the driver measures).
+#   4  configs[3]: NeRF-MVL-like object scan - 256 x 1800 pano, fov (15, 40) deg, scale 0.005 (configs/nerf_mvl.txt),
+#      spherical-harmonics (degree 4) direction encoding in the head, alpha_i = 1, bound 1, occupancy march.
+#   5  configs[4]: large-bound scene - bound 4 (cascade 3, 768 KiB bitfield), max_steps 128, 16384 rays per GPU and step
+#      (the 8-GPU roofline sweep; the MLPs run in fp16 on the tensor cores with fp32 accumulation - see DESIGN.md on bf16).
+WORKLOADS = {
+    2: dict(rays=4096, field={}, seq={}, text=WORKLOAD),
+    4: dict(rays=4096, field=dict(dir_encoding="sh", sh_degree=4, min_near_lidar=0.005, alpha_i=1.0),
+            seq=dict(H=256, W=1800, fov_up=15.0, fov=40.0, scale=0.005), metric="training rays/s (256x1800 pano)",
+            text=("NeRF-MVL-like synthetic 256x1800 pano x 8 frames (fov 15/40 deg, scale 0.005), hashgrid L16 F2 T2^19 "
+                  "res16->32768 + ffmlp 64x2 sigma + ffmlp 64x2 head with SH(4) direction encoding, 4096 rays/GPU/step, "
+                  "occupancy march max_steps=1024 dt_gamma=0, fwd+bwd+Adam+grid refresh/16 steps")),
+    5: dict(rays=16384, field=dict(bound=4.0, max_steps=128, min_near_lidar=4.0 / 92.7),
+            seq=dict(scale=4.0 / 92.7),
+            text=("large-bound synthetic 64x1024 pano x 8 frames, bound 4 (cascade 3), hashgrid L16 F2 T2^19 res16->32768 + "
+                  "ffmlp 64x2 sigma + ffmlp 64x2 lidar head, 16384 rays/GPU/step, occupancy march max_steps=128 dt_gamma=0, "
+                  "fwd+bwd+Adam+grid refresh/16 steps")),
+}
+
 
 def parse():
     ap = argparse.ArgumentParser()
@@ -34,7 +53,8 @@ def parse():
     ap.add_argument("--steps", type=int, default=400)
     ap.add_argument("--warmup", type=int, default=8)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cuda"])
-    ap.add_argument("--rays", type=int, default=RAYS)
+    ap.add_argument("--rays", type=int, default=None, help="rays per GPU and step (default: the configuration's)")
+    ap.add_argument("--config", type=int, default=2, choices=sorted(WORKLOADS), help="BASELINE.json configuration (see WORKLOADS)")
     ap.add_argument("--frames", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-profile", action="store_true")
@@ -143,20 +163,27 @@ def cpu_reference_leg(args, threads, rays, steps, warm=1):
     orc.build()
     orc.set_threads(threads)
     torch.set_num_threads(threads)
-    cfg = FieldConfig()
-    seq = SyntheticLidarSequence(n_frames=2, device="cpu")
+    wl = WORKLOADS[args.config]
+    cfg = FieldConfig(**wl["field"])
+    seq = SyntheticLidarSequence(n_frames=2, device="cpu", **wl["seq"])
     rng = np.random.default_rng(0)
     params = fs.FieldParams(cfg)
     params.P[:params.n_table] = rng.uniform(-1e-4, 1e-4, params.n_table).astype(np.float32)
     params.P[params.n_table:] = rng.uniform(-0.2165, 0.2165, params.n_sigma + params.n_head).astype(np.float32)
-    # occupancy prior from the GT returns (same construction as the GPU arm)
+    # occupancy prior from the GT returns (same construction as the GPU arm): in every cascade, the cells containing a
+    # return, dilated by one
     pts = seq.surface_points().numpy()
     H = cfg.grid_size
-    cell = np.clip((0.5 * (pts / cfg.bound + 1) * H).astype(np.int64), 0, H - 1)
     offs = np.stack(np.meshgrid(*([np.arange(-1, 2)] * 3), indexing="ij"), -1).reshape(-1, 3)
-    cell = np.unique(np.clip(cell[:, None, :] + offs[None], 0, H - 1).reshape(-1, 3), axis=0)
-    bits = np.zeros(H ** 3, bool)
-    bits[orc.morton3D(cell.astype(np.int32)).astype(np.int64)] = True
+    bits = np.zeros(cfg.cascade * H ** 3, bool)
+    for cas in range(cfg.cascade):
+        bound = min(2.0 ** cas, cfg.bound)
+        sel = pts[(np.abs(pts) <= bound).all(-1)]
+        if len(sel) == 0:
+            continue
+        cell = np.clip((0.5 * (sel / bound + 1) * H).astype(np.int64), 0, H - 1)
+        cell = np.unique(np.clip(cell[:, None, :] + offs[None], 0, H - 1).reshape(-1, 3), axis=0)
+        bits[cas * H ** 3 + orc.morton3D(cell.astype(np.int32)).astype(np.int64)] = True
     bitfield = np.packbits(bits.reshape(-1, 8), axis=1, bitorder="little").reshape(-1)
     gen = torch.Generator().manual_seed(0)
     times, n_samples = [], 0
@@ -192,11 +219,11 @@ def main():
         steps = max(1, min(args.steps, 24))
         warm = max(1, min(args.warmup, 6))
         cb, med = cpu_reference_leg(args, threads, args.cpu_rays, steps, warm)
-        out = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": "rays/s", "n_gpus": args.gpus,
+        out = {"impl": "reference", "metric": WORKLOADS[args.config].get("metric", METRIC), "value": cb["value"], "unit": "rays/s", "n_gpus": args.gpus,
                "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
                "ms_per_step": med * 1e3, "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None, "dtype": "f32 (fp16-rounded tables/MLP) on CPU", "data": "synthetic",
-               "config": bench_config(),
+               "config": bench_config(args.config),
                "detail": {"rays_per_step_sampled": args.cpu_rays,
                           "note": "reference algorithm on host CPU cores (oracle port; the reference's own CUDA/Python "
                                   "path cannot travel to this box); each step is a bounded --cpu-rays sample of the "
@@ -218,8 +245,11 @@ def main():
     clocks.start()        # forked NOW (before the engine is built): it is long past its start-up when the timing begins
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N = args.rays
-    cfg = FieldConfig()
+    wl = WORKLOADS[args.config]
+    N = args.rays or wl["rays"]
+    cfg = FieldConfig(**wl["field"])
+    if os.environ.get("LNB_FUSED_GATHER") == "0":         # A/B switch: two-kernel forward instead of the persistent kernel
+        cfg.fused_gather = False
     if os.environ.get("LNB_COMPACT_BACKWARD") == "0":     # A/B switch for the diagnostics in profiles/
         cfg.compact_backward = False
     if os.environ.get("LNB_LATE_GRAD_ZERO") == "0":
@@ -230,7 +260,9 @@ def main():
         cfg.overlap_exchange = False
     if os.environ.get("LNB_FUSED_EXCHANGE") == "0":
         cfg.fused_exchange = False
-    seq = SyntheticLidarSequence(n_frames=args.frames, device=dev)
+    if os.environ.get("LNB_MULTICAST_EXCHANGE") == "0":
+        cfg.multicast_exchange = False
+    seq = SyntheticLidarSequence(n_frames=args.frames, device=dev, **wl["seq"])
     # Sample rows: the WORST case of this configuration, so that no ray is ever dropped for lack of rows however the
     # occupancy grid evolves during the run (a ray holds at most (far - near) / dt_min + 1 = 256 samples at dt_gamma = 0;
     # the reference sizes its buffers from a running mean and silently skips the rays that do not fit,
@@ -274,11 +306,11 @@ def main():
         del eng
         torch.cuda.empty_cache()
         r = api_b2_leg(seq, dev, N, args.steps, args.warmup)
-        out = {"metric": METRIC, "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
+        out = {"metric": WORKLOADS[args.config].get("metric", METRIC), "value": r["rays_per_s"], "unit": "rays/s", "n_gpus": 1, "steps": args.steps,
                "warmup": max(args.warmup, 12), "ms_per_step": r["ms_per_step"], "higher_is_better": True,
                "scaling": "weak", "vs_baseline": None,
                "dtype": "f16 tables+MLP (fp32 accumulate) / f32 march+composite / torch fp32 Adam", "data": "synthetic",
-               "config": bench_config(), "detail": {"api": "b2", **r},
+               "config": bench_config(args.config), "detail": {"api": "b2", **r},
                "e2e": {"value": r["rays_per_s"], "unit": "rays/s", "h2d_bytes_per_step": N * 9 * 4,
                        "d2h_bytes_per_step": 4}, "clocks": clocks.stop()}
         print(json.dumps(out), flush=True)
@@ -384,10 +416,10 @@ def main():
         kernels, roof, roof_l2 = profile_kernels(eng, pool, load)
 
     ref_cuda = None
-    if rank == 0 and world == 1 and not args.no_reference_cuda:
+    if rank == 0 and world == 1 and not args.no_reference_cuda and args.config == 2:
         ref_cuda = reference_cuda_inline(eng, pool, load)
     api_b2 = None
-    if rank == 0 and world == 1 and not args.no_api_b2:
+    if rank == 0 and world == 1 and not args.no_api_b2 and args.config == 2:
         try:
             api_b2 = api_b2_leg(seq, dev, N, 40, 12)
         except Exception as e:   # noqa: BLE001 - an optional extra leg must never sink the measurement
@@ -395,19 +427,22 @@ def main():
 
     if rank == 0:
         value = world * N * args.steps / (ms * 1e-3)
-        out = {"metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        out = {"metric": WORKLOADS[args.config].get("metric", METRIC), "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": "f16 tables+MLP (fp32 accumulate) / f32 march+composite+Adam",
                "data": "synthetic",
-               "config": bench_config(),
+               "config": bench_config(args.config),
                "detail": {"rays_per_gpu": N, "samples_per_step": produced, "samples_per_ray": produced / N,
                           "live_samples_per_step": live, "sample_budget_M": eng.M, "rays_dropped_last_step": dropped,
                           "params": eng.n_params, "grid_refresh_ms": refresh_ms, "grid_refresh_every": cfg_interval,
                           "timing": {"repeats": repeats, "steps_per_block": args.steps, "reported": "median block",
                                      "untimed_spin_steps": spun, "attempts": attempts,
                                      "value_ge_e2e": consistent},
-                          "parallelism": (f"dp{world} (" + ("ONE peer-memory kernel over NVLink: reduce-scatter fp32 grad + sharded Adam + "
-                                                          "all-gather fp16 params" if eng._peer is not None else
+                          "parallelism": (f"dp{world} (" + (("ONE kernel through NVSwitch multicast (NVLS): multimem.ld_reduce of the fp32 "
+                                                           "grad shard + sharded Adam + multimem.st of the fp16 params"
+                                                           if eng._peer.get("mc") else
+                                                           "ONE peer-memory kernel over NVLink: reduce-scatter fp32 grad + sharded "
+                                                           "Adam + all-gather fp16 params") if eng._peer is not None else
                                                           "NCCL reduce-scatter fp32 grad -> sharded Adam -> all-gather fp16 params")
                                           + (", overlapped with the next step's march)" if cfg.overlap_exchange else ")"))
                           if world > 1 else "single",
@@ -498,9 +533,10 @@ def api_b2_leg(seq, dev, n_rays, steps, warmup, seed=0):
                     "GradScaler -> torch.optim.Adam; pinned host batch in, loss.item() out, every step (eager launches)"}
 
 
-def bench_config():
+def bench_config(config_id=2):
     """The `config` object: identical in both arms (the driver compares them)."""
-    return {"workload": WORKLOAD, "rays_per_step_per_gpu": RAYS,
+    wl = WORKLOADS[config_id]
+    return {"workload": wl["text"], "baseline_config": config_id, "rays_per_step_per_gpu": wl["rays"],
             "l2": "no explicit flush: every step streams ~410 MB of Adam state and a 55 MB gradient memset through the "
                   "126 MB L2 and draws a new ray batch (inputs larger than L2)"}
 
@@ -569,7 +605,7 @@ def reference_cuda_leg(args, eng, pool, load, world):
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / steps
-    out = {"impl": "reference-cuda", "metric": METRIC, "value": eng.N / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
+    out = {"impl": "reference-cuda", "metric": WORKLOADS[args.config].get("metric", METRIC), "value": eng.N / (ms * 1e-3), "unit": "rays/s", "n_gpus": 1,
            "steps": steps, "warmup": 3, "ms_per_step": ms, "higher_is_better": True, "data": "synthetic",
            "dtype": "f16 tables+MLP (fp16 accumulate) / f32 march+composite / torch Adam",
            "config": {"workload": WORKLOAD, "rays_per_gpu": eng.N, "sample_rows_M": eng.M,

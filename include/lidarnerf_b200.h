@@ -269,6 +269,14 @@ int lnb_dp_adam_exchange(const void *const *grad_ptrs, void *const *half_ptrs, u
                          float *exp_avg_shard, float *exp_avg_sq_shard, size_t shard_lo, size_t shard_n, float lr,
                          float beta1, float beta2, float eps, float bias_correction1, float bias_correction2,
                          float grad_scale, lnb_stream_t stream);
+/* The same exchange through NVSwitch multicast / in-switch reduction (NVLS): `grad_multicast` / `half_multicast` are the
+ * MULTICAST addresses of the flat fp32 gradient / fp16 shadow (torch symmetric memory `multicast_ptr`); the gradient sum
+ * of this rank's shard comes back from one multimem.ld_reduce per 16 bytes, the updated parameters reach every rank
+ * with one multimem.st.  shard_lo and shard_n must be multiples of 8. */
+int lnb_dp_adam_exchange_mc(const void *grad_multicast, void *half_multicast, float *params_shard, float *exp_avg_shard,
+                            float *exp_avg_sq_shard, size_t shard_lo, size_t shard_n, float lr, float beta1, float beta2,
+                            float eps, float bias_correction1, float bias_correction2, float grad_scale,
+                            lnb_stream_t stream);
 int lnb_adam_step_dev(float *params, float *grad, float *exp_avg, float *exp_avg_sq, void *params_half, size_t n,
                       float beta1, float beta2, float eps, const float *hyper_dev, int zero_grad, lnb_stream_t stream);
 

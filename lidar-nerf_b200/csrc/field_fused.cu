@@ -34,13 +34,21 @@ namespace {
 constexpr uint32_t kGatherWarps = 16;
 constexpr uint32_t kGatherThreads = kGatherWarps * 32;
 constexpr uint32_t kGroups = 2;                        // epilogue groups (128 threads, thread = tile row)
-constexpr uint32_t kSlotsPerGroup = 2;                 // tiles a group keeps in flight, processed phase by phase in turn
+// Measured on B200 (385 k samples, profiles/r02_fused_forward_diag.txt): one tile per epilogue group (2 tiles in flight)
+// 164 us, two per group (4 in flight) 181 us - the extra tiles in flight only lengthen the gather's wait for a free stage.
+#ifndef LNB_FUSED_SLOTS_PER_GROUP
+#define LNB_FUSED_SLOTS_PER_GROUP 1
+#endif
+#ifndef LNB_FUSED_STAGES
+#define LNB_FUSED_STAGES 3
+#endif
+constexpr uint32_t kSlotsPerGroup = LNB_FUSED_SLOTS_PER_GROUP;   // tiles a group keeps in flight, processed phase by phase in turn
 constexpr uint32_t kSlots = kGroups * kSlotsPerGroup;  // tiles in flight in the MLP part of one CTA
 constexpr uint32_t kGroupThreads = 128;
 constexpr uint32_t kEpiWarp0 = kGatherWarps;           // first epilogue warp (multiple of 4: TMEM lane quadrants)
 constexpr uint32_t kMmaWarpIdx = kEpiWarp0 + kGroups * 4;
 constexpr uint32_t kFusedThreads = (kMmaWarpIdx + 1) * 32;      // 800
-constexpr uint32_t kStages = 3;                        // operand tiles between the gather and the first MLP layer
+constexpr uint32_t kStages = LNB_FUSED_STAGES;         // operand tiles between the gather and the first MLP layer
 constexpr uint32_t kTmemColsPerSlot = 128;             // [0,64) hidden accumulator, [64,80) output accumulator
 constexpr uint32_t kCoordBufs = 2;
 
@@ -73,7 +81,8 @@ struct FusedArgs {
     __half *enc, *fb_s, *sig_out, *fb_h;
     float *sigma, *rgb;
     uint32_t dbg;     // diagnostics only (LNB_FUSED_DBG, scripts/diag_fused_fwd.py): bit 0 = gather without table loads,
-                      // bit 1 = no saved-activation / enc stores, bit 2 = epilogue skips the per-layer math
+                      // bit 1 = no saved-activation / enc stores, bit 2 = epilogue skips the per-layer math,
+                      // bit 3 = gather warps skip the cell / index / blend arithmetic as well (protocol only)
 };
 
 __device__ __forceinline__ void sts32(uint32_t addr, uint32_t v) {
@@ -194,7 +203,11 @@ k_field_fused_fwd(const FusedArgs a) {
             mbar_init(bar_xempty + 8 * s, 1 + 4);                 // tcgen05.commit + one arrival per epilogue warp
         }
         for (uint32_t q = 0; q < kSlots; ++q) {
+#ifdef LNB_FUSED_THREAD_ARRIVE
+            mbar_init(bar_ready + 8 * q, kGroupThreads);
+#else
             mbar_init(bar_ready + 8 * q, 4);                      // one arrival per epilogue warp of the owning group
+#endif
             mbar_init(bar_done + 8 * q, 1);
         }
         mbar_init(bar_w, 1);
@@ -308,6 +321,7 @@ k_field_fused_fwd(const FusedArgs a) {
                 // L2 latency that 48 warps cover in the stand-alone encoder kernel)
 #pragma unroll
                 for (uint32_t pair = 0; pair < kRows / 64; ++pair) {
+                    if (a.dbg & 8u) break;
                     const uint32_t sl_a = pair * 64 + lane, sl_b = sl_a + 32;
                     const Cell<D> ca = locate_sample(in, sl_a, g), cb = locate_sample(in, sl_b, g);
                     uint32_t ra[8], rb[8];
@@ -347,15 +361,28 @@ k_field_fused_fwd(const FusedArgs a) {
                 *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * cpr + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
             }
         };
+#ifdef LNB_FUSED_THREAD_ARRIVE
+        auto publish = [&](uint32_t bar) {
+            fence_proxy_async();
+            fence_before_sync();
+            mbar_arrive(bar);
+        };
+        auto arrive_warp = [&](uint32_t bar) { mbar_arrive(bar); };
+#else
         auto publish = [&](uint32_t bar) {                  // this warp's rows of an operand tile are in place
             fence_proxy_async();
             fence_before_sync();
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
+        auto arrive_warp = [&](uint32_t bar) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar);
+        };
+#endif
 
         for (uint32_t q = 0; q < kSlotsPerGroup; ++q)       // tensor memory of the group's slots is free
-            if (g * kSlotsPerGroup + q < n_my && lane == 0) mbar_arrive(bar_ready + 8 * (g * kSlotsPerGroup + q));
+            if (g * kSlotsPerGroup + q < n_my) arrive_warp(bar_ready + 8 * (g * kSlotsPerGroup + q));
 
         for (uint32_t k0 = g * kSlotsPerGroup; k0 < n_my; k0 += kSlots) {
             const uint32_t nt = min(kSlotsPerGroup, n_my - k0);
@@ -424,8 +451,7 @@ k_field_fused_fwd(const FusedArgs a) {
                         const float x1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
                         reinterpret_cast<float2 *>(a.rgb)[r] = make_float2(1.f / (1.f + __expf(-x0)), 1.f / (1.f + __expf(-x1)));
                         fence_before_sync();                 // this tile's TMEM reads are ordered before the next tile's MMAs
-                        __syncwarp();
-                        if (k0 + t + kSlots < n_my && lane == 0) mbar_arrive(ready);   // the slot's next tile may start
+                        if (k0 + t + kSlots < n_my) arrive_warp(ready);                // the slot's next tile may start
                     }
                 }
             }

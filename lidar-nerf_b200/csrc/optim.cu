@@ -117,6 +117,57 @@ k_dp_adam_exchange(PeerPtrs pp, uint32_t world, float *__restrict__ p, float *__
     }
 }
 
+// The same exchange through the NVSwitch's multicast / in-switch reduction (NVLS): the flat gradient and the fp16 shadow
+// are additionally mapped at MULTICAST addresses (torch symmetric memory: `multicast_ptr`); one `multimem.ld_reduce`
+// returns the sum over all ranks of a 16-byte gradient vector (the switch reduces, 1/world of the bytes of the peer-load
+// form arrive at this GPU) and one `multimem.st` writes the updated parameters into every rank's shadow (the switch
+// replicates).  Per rank and parameter the wire carries 4 B / world in + 2 B / world out instead of
+// (world - 1) / world x (4 + 2) B.
+__device__ __forceinline__ float4 mc_ld_reduce_f32x4(const float *mc) {
+    float4 r;
+    asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(mc)
+                 : "memory");
+    return r;
+}
+__device__ __forceinline__ void mc_st_b128(void *mc, uint4 v) {
+    asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(mc), "f"(__uint_as_float(v.x)),
+                 "f"(__uint_as_float(v.y)), "f"(__uint_as_float(v.z)), "f"(__uint_as_float(v.w))
+                 : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads)
+k_dp_adam_exchange_mc(const float *__restrict__ grad_mc, __half *__restrict__ half_mc, float *__restrict__ p,
+                      float *__restrict__ m, float *__restrict__ v, size_t lo, size_t n, AdamArgs a) {
+    const size_t n8 = n / 8;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    float4 *p4 = reinterpret_cast<float4 *>(p), *m4 = reinterpret_cast<float4 *>(m), *v4 = reinterpret_cast<float4 *>(v);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+        const float4 g0 = mc_ld_reduce_f32x4(grad_mc + lo + 8 * i), g1 = mc_ld_reduce_f32x4(grad_mc + lo + 8 * i + 4);
+        float4 pa = p4[2 * i], pb = p4[2 * i + 1], ma = m4[2 * i], mb = m4[2 * i + 1], va = v4[2 * i], vb = v4[2 * i + 1];
+        adam_one(pa.x, g0.x, ma.x, va.x, a);
+        adam_one(pa.y, g0.y, ma.y, va.y, a);
+        adam_one(pa.z, g0.z, ma.z, va.z, a);
+        adam_one(pa.w, g0.w, ma.w, va.w, a);
+        adam_one(pb.x, g1.x, mb.x, vb.x, a);
+        adam_one(pb.y, g1.y, mb.y, vb.y, a);
+        adam_one(pb.z, g1.z, mb.z, vb.z, a);
+        adam_one(pb.w, g1.w, mb.w, vb.w, a);
+        p4[2 * i] = pa, p4[2 * i + 1] = pb;
+        m4[2 * i] = ma, m4[2 * i + 1] = mb;
+        v4[2 * i] = va, v4[2 * i + 1] = vb;
+        const __half2 h0 = __floats2half2_rn(pa.x, pa.y), h1 = __floats2half2_rn(pa.z, pa.w);
+        const __half2 h2 = __floats2half2_rn(pb.x, pb.y), h3 = __floats2half2_rn(pb.z, pb.w);
+        uint4 packed;
+        packed.x = *reinterpret_cast<const unsigned *>(&h0);
+        packed.y = *reinterpret_cast<const unsigned *>(&h1);
+        packed.z = *reinterpret_cast<const unsigned *>(&h2);
+        packed.w = *reinterpret_cast<const unsigned *>(&h3);
+        mc_st_b128(half_mc + lo + 8 * i, packed);
+    }
+}
+
 __global__ void k_adam_set_hyper(float *hyper, float lr, float inv_bc1, float inv_sqrt_bc2, float gscale, float enable) {
     hyper[0] = lr, hyper[1] = inv_bc1, hyper[2] = inv_sqrt_bc2, hyper[3] = gscale, hyper[4] = enable;
 }
@@ -195,6 +246,25 @@ extern "C" int lnb_dp_adam_exchange(const void *const *grad_ptrs, void *const *h
     const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
     k_dp_adam_exchange<<<blocks, kThreads, 0, as_stream(stream)>>>(pp, world, params_shard, exp_avg_shard, exp_avg_sq_shard,
                                                                   shard_lo, shard_n, a);
+    count_launch();
+    return launch_status();
+}
+
+extern "C" int lnb_dp_adam_exchange_mc(const void *grad_multicast, void *half_multicast, float *params_shard,
+                                       float *exp_avg_shard, float *exp_avg_sq_shard, size_t shard_lo, size_t shard_n,
+                                       float lr, float beta1, float beta2, float eps, float bias_correction1,
+                                       float bias_correction2, float grad_scale, lnb_stream_t stream) {
+    if (!grad_multicast || !half_multicast || !params_shard || !exp_avg_shard || !exp_avg_sq_shard)
+        return LNB_ERR_INVALID_ARGUMENT;
+    if (shard_n % 8 != 0 || shard_lo % 8 != 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (bias_correction1 == 0.f || bias_correction2 <= 0.f) return LNB_ERR_INVALID_ARGUMENT;
+    if (shard_n == 0) return LNB_OK;
+    AdamArgs a{lr, beta1, beta2, eps, 1.f / bias_correction1, 1.f / sqrtf(bias_correction2), grad_scale};
+    const size_t want = (shard_n / 8 + kThreads - 1) / kThreads;
+    const unsigned blocks = (unsigned)(want < 1 ? 1 : (want > 148 * 8 ? 148 * 8 : want));
+    k_dp_adam_exchange_mc<<<blocks, kThreads, 0, as_stream(stream)>>>(static_cast<const float *>(grad_multicast),
+                                                                     static_cast<__half *>(half_multicast), params_shard,
+                                                                     exp_avg_shard, exp_avg_sq_shard, shard_lo, shard_n, a);
     count_launch();
     return launch_status();
 }

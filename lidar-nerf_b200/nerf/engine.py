@@ -92,7 +92,10 @@ class LidarFieldEngine:
                 Ps.copy_(self.Ph)
                 ptr_t = C.c_void_p * self.ex.world
                 self._peer = dict(hG=hG, hP=hP, g=ptr_t(*[int(x) for x in hG.buffer_ptrs]),
-                                  h=ptr_t(*[int(x) for x in hP.buffer_ptrs]))
+                                  h=ptr_t(*[int(x) for x in hP.buffer_ptrs]), mc=None)
+                mc_g, mc_h = int(getattr(hG, "multicast_ptr", 0) or 0), int(getattr(hP, "multicast_ptr", 0) or 0)
+                if c.multicast_exchange and mc_g and mc_h:
+                    self._peer["mc"] = (mc_g, mc_h)          # NVLS: in-switch reduce-scatter + multicast all-gather
                 self.G, self.Ph = Gs, Ps
                 torch.cuda.synchronize(dev)
                 hG.barrier(channel=0, timeout_ms=20000)        # every rank's buffers are initialised
@@ -457,11 +460,20 @@ class LidarFieldEngine:
             # all ranks' gradients complete -> [peer reduce-scatter + Adam + peer all-gather] -> all shadows complete
             pr = self._peer
             pr["hG"].barrier(channel=0, timeout_ms=20000)
-            _ck(lib.lnb_dp_adam_exchange(pr["g"], pr["h"], u32(self.ex.world), vp(self.P.data_ptr()),
-                                         vp(self.m.data_ptr()), vp(self.v.data_ptr()), sz(self.ex.lo), sz(self.ex.shard),
-                                         f32(lr), f32(c.beta1), f32(c.beta2), f32(c.eps),
-                                         f32(1.0 - c.beta1 ** self.step_count), f32(1.0 - c.beta2 ** self.step_count),
-                                         f32(dp.grad_scale(c.loss_scale)), self._s()), "dp_adam_exchange")
+            if pr["mc"] is not None:
+                _ck(lib.lnb_dp_adam_exchange_mc(vp(pr["mc"][0]), vp(pr["mc"][1]), vp(self.P.data_ptr()),
+                                                vp(self.m.data_ptr()), vp(self.v.data_ptr()), sz(self.ex.lo),
+                                                sz(self.ex.shard), f32(lr), f32(c.beta1), f32(c.beta2), f32(c.eps),
+                                                f32(1.0 - c.beta1 ** self.step_count),
+                                                f32(1.0 - c.beta2 ** self.step_count),
+                                                f32(dp.grad_scale(c.loss_scale)), self._s()), "dp_adam_exchange_mc")
+            else:
+                _ck(lib.lnb_dp_adam_exchange(pr["g"], pr["h"], u32(self.ex.world), vp(self.P.data_ptr()),
+                                             vp(self.m.data_ptr()), vp(self.v.data_ptr()), sz(self.ex.lo),
+                                             sz(self.ex.shard), f32(lr), f32(c.beta1), f32(c.beta2), f32(c.eps),
+                                             f32(1.0 - c.beta1 ** self.step_count),
+                                             f32(1.0 - c.beta2 ** self.step_count),
+                                             f32(dp.grad_scale(c.loss_scale)), self._s()), "dp_adam_exchange")
             pr["hG"].barrier(channel=1, timeout_ms=20000)
             if not c.late_grad_zero:
                 self.G.zero_()

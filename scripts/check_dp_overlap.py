@@ -17,9 +17,9 @@ dev = torch.device(f"cuda:{local}")
 dist.init_process_group("nccl", device_id=dev)
 seq = SyntheticLidarSequence(H=16, W=256, n_frames=2, device=dev)
 out = {}
-for overlap, fused in ((False, False), (True, False), (True, True)):
+for overlap, fused, mc in ((False, False, False), (True, False, False), (True, True, False), (True, True, True)):
     cfg = FieldConfig(log2_hashmap_size=15, desired_resolution=2048, grid_update_interval=4, lr=5e-3, perturb=False,
-                      overlap_exchange=overlap, fused_exchange=fused)
+                      overlap_exchange=overlap, fused_exchange=fused, multicast_exchange=mc)
     eng = LidarFieldEngine(cfg, 512, device=dev, sample_budget=512 * 128)
     eng.seed_occupancy_from_points(seq.surface_points())
     gen = torch.Generator().manual_seed(100 + rank)
@@ -30,10 +30,11 @@ for overlap, fused in ((False, False), (True, False), (True, True)):
         eng.train_step(use_graph=True)
     eng.flush()
     torch.cuda.synchronize()
-    out[(overlap, fused)] = (eng.Ph.clone().float(), eng.bitfield.clone(), eng.step_count, eng._peer is not None)
+    out[(overlap, fused, mc)] = (eng.Ph.clone().float(), eng.bitfield.clone(), eng.step_count,
+                                 ("multicast (NVLS)" if eng._peer.get("mc") else "peer loads/stores") if eng._peer is not None else "no")
     del eng
-b = out[(False, False)]
-for key in ((True, False), (True, True)):
+b = out[(False, False, False)]
+for key in ((True, False, False), (True, True, False), (True, True, True)):
     a = out[key]
     assert a[2] == b[2] == 11
     assert torch.equal(a[1], b[1]), "density-grid refreshes saw different parameters"
@@ -42,7 +43,7 @@ for key in ((True, False), (True, True)):
     ref = a[0].clone()                   # every rank holds the same parameters
     dist.broadcast(ref, src=0)
     assert torch.equal(ref, a[0]), "ranks diverged"
-    print(f"[rank {rank}] OK overlap={key[0]} fused={key[1]} (peer memory in use: {a[3]}): == sequential NCCL schedule "
+    print(f"[rank {rank}] OK overlap={key[0]} fused={key[1]} multicast={key[2]} (peer memory in use: {a[3]}): == sequential NCCL schedule "
           f"(rel {rel:.2e}), ranks identical", flush=True)
 dist.barrier()
 dist.destroy_process_group()

@@ -65,7 +65,9 @@ def main():
         for name, (fn, a) in rec.calls.items():
             if name == "lnb_field_fused_forward":
                 for dbg, what in ((0, "full"), (1, "gather without table loads"), (2, "no enc/activation stores"),
-                                  (3, "no loads, no stores"), (4, "no epilogue math/stores"), (7, "skeleton: barriers + MMAs only")):
+                                  (3, "no loads, no stores"), (4, "no epilogue math/stores"), (7, "skeleton: barriers + MMAs + gather index math"),
+                                  (15, "protocol only: barriers + MMAs"), (9, "MLP only: no gather work at all"),
+                                  (6, "gather only: no epilogue math/stores")):
                     os.environ["LNB_FUSED_DBG_LIVE"] = str(dbg)
                     print(f"  {name} [{what}]: {best_of(fn, a):7.1f} us")
                 os.environ["LNB_FUSED_DBG_LIVE"] = "0"

@@ -11,9 +11,11 @@ from test_gpu_engine import _run_engine_only
 
 DEV = "cuda:0"
 n_rays = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+extra = dict(dir_encoding="sh", sh_degree=4) if "sh" in sys.argv[2:] else {}
 out = {}
 for fg in (False, True):
-    cfg = check_engine.small_config(fused_gather=fg, perturb=False, log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
+    cfg = check_engine.small_config(fused_gather=fg, perturb=False, log2_hashmap_size=19, desired_resolution=32768, max_steps=1024,
+                                    **extra)
     eng = _run_engine_only(cfg, n_rays)
     n = int(eng.counter[0])
     rays = eng.rays.cpu().numpy()

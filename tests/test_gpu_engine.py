@@ -89,17 +89,17 @@ def _run_engine_only(cfg, n_rays, seed=11):
     return eng
 
 
-def test_sh_direction_head_matches_cpu_restatement():
+@pytest.mark.parametrize("fused_gather", [True, False])
+def test_sh_direction_head_matches_cpu_restatement(fused_gather):
     """BASELINE config 4: the head's direction encoding is real spherical harmonics of degree 4 (network.py:64,
     network_tcnn.py:74-80) instead of the frequency encoding - a per-ray bias like the frequency terms, 16 + 15 -> 32
     head inputs.  Whole step (loss, outputs, all gradients) against the CPU restatement, both forward variants."""
     from oracle import check_engine
-    for fused_gather in (True, False):
-        cfg = check_engine.small_config(dir_encoding="sh", sh_degree=4, fused_gather=fused_gather)
-        assert cfg.head_in_dim == 32 and cfg.dir_code == 0x104
-        eng, gpu, cpu = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg, seed=5)
-        assert eng.fused and eng.fused_gather == fused_gather and eng.n_head == 64 * (32 + 64 + 16)
-        check_engine.compare(gpu, cpu, eng.n_table)
+    cfg = check_engine.small_config(dir_encoding="sh", sh_degree=4, fused_gather=fused_gather)
+    assert cfg.head_in_dim == 32 and cfg.dir_code == 0x104
+    eng, gpu, cpu = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg, seed=5)
+    assert eng.fused and eng.fused_gather == fused_gather and eng.n_head == 64 * (32 + 64 + 16)
+    check_engine.compare(gpu, cpu, eng.n_table)
 
 
 def test_lidar_loss_kernel_with_patch_term_matches_reference_train_step(golden_dir):
@@ -499,3 +499,20 @@ def test_compat_install_registers_reference_module_names():
     from shencoder import SHEncoder            # noqa: F401
     import _raymarching, _gridencoder, _ffmlp  # noqa: F401,E401
     assert callable(sys.modules["raymarching"].march_rays_train)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs 2 GPUs (gpurun --gpus 2)")
+def test_peer_memory_and_multicast_exchange_equal_nccl_on_two_gpus():
+    """2 ranks under torchrun (scripts/check_dp_overlap.py): the overlapped NCCL schedule, the peer-memory exchange kernel
+    and the NVSwitch-multicast exchange kernel all train exactly like the sequential NCCL schedule and leave every rank
+    with bit-identical parameters."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    port = 29600 + os.getpid() % 300
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port),
+                        os.path.join(root, "scripts", "check_dp_overlap.py")], capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert r.stdout.count("OK overlap=True fused=True") >= 2, r.stdout[-3000:]
