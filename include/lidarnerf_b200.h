@@ -359,6 +359,10 @@ int lnb_field_sigma_out_grad(const float *g_sigma, const void *sigma_out, const 
 /* get_lidar_rays (dataset/base_dataset.py:85-100): pose [3x4 or 4x4 row-major], inds [N] flat pixel ids */
 int lnb_lidar_rays(const float *pose, const int32_t *inds, uint32_t N, uint32_t H, uint32_t W, float fov_up,
                    float fov, float *rays_o, float *rays_d, lnb_stream_t stream);
+/* One training batch from a frame resident on the device - the per-step collate of kitti360_dataset.py:123-159:
+ * lnb_lidar_rays + gather of the sampled pixels' ground-truth rows from image [H*W, 3] (ray-drop, intensity, depth) */
+int lnb_lidar_batch(const float *pose, const int32_t *inds, const float *image, uint32_t N, uint32_t H, uint32_t W,
+                    float fov_up, float fov, float *rays_o, float *rays_d, float *gt, lnb_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
  * Fused LiDAR field network (density MLP -> LiDAR head) - same arithmetic as

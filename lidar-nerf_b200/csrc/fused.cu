@@ -247,6 +247,29 @@ k_lidar_rays(const float *__restrict__ pose, const int32_t *__restrict__ inds, u
     }
 }
 
+// One training batch from a frame that lives on the device (what the reference's collate does with torch ops per step,
+// kitti360_dataset.py:123-159): rays of the sampled pixels (get_lidar_rays) + their ground-truth rows gathered from the
+// frame's range image [H*W, 3] = (ray-drop mask, intensity, depth * scale).
+__global__ void __launch_bounds__(kThreads)
+k_lidar_batch(const float *__restrict__ pose, const int32_t *__restrict__ inds, const float *__restrict__ image, uint32_t N,
+              uint32_t H, uint32_t W, float fov_up, float fov, float *__restrict__ rays_o, float *__restrict__ rays_d,
+              float *__restrict__ gt) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const uint32_t idx = (uint32_t)inds[n];
+    const float j = (float)(idx / W), i = (float)(idx % W);
+    const float pi = 3.14159265358979323846f;
+    const float beta = -(i - (float)W / 2) / (float)W * 2 * pi;
+    const float alpha = (fov_up - j / (float)H * fov) / 180 * pi;
+    const float dir[3] = {cosf(alpha) * cosf(beta), cosf(alpha) * sinf(beta), sinf(alpha)};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        rays_d[n * 3 + r] = pose[r * 4 + 0] * dir[0] + pose[r * 4 + 1] * dir[1] + pose[r * 4 + 2] * dir[2];
+        rays_o[n * 3 + r] = pose[r * 4 + 3];
+        gt[n * 3 + r] = __ldg(image + (size_t)idx * 3 + r);
+    }
+}
+
 inline unsigned nblk(uint64_t n) { return (unsigned)((n + kThreads - 1) / kThreads); }
 
 }  // namespace
@@ -349,6 +372,15 @@ int lnb_lidar_rays(const float *pose, const int32_t *inds, uint32_t N, uint32_t 
     if (!pose || !inds || !rays_o || !rays_d || H == 0 || W == 0) return LNB_ERR_INVALID_ARGUMENT;
     if (N == 0) return LNB_OK;
     k_lidar_rays<<<nblk(N), kThreads, 0, as_stream(stream)>>>(pose, inds, N, H, W, fov_up, fov, rays_o, rays_d);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_lidar_batch(const float *pose, const int32_t *inds, const float *image, uint32_t N, uint32_t H, uint32_t W,
+                    float fov_up, float fov, float *rays_o, float *rays_d, float *gt, lnb_stream_t stream) {
+    if (!pose || !inds || !image || !rays_o || !rays_d || !gt || H == 0 || W == 0) return LNB_ERR_INVALID_ARGUMENT;
+    if (N == 0) return LNB_OK;
+    k_lidar_batch<<<nblk(N), kThreads, 0, as_stream(stream)>>>(pose, inds, image, N, H, W, fov_up, fov, rays_o, rays_d, gt);
     count_launch();
     return launch_status();
 }

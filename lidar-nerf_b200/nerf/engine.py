@@ -530,6 +530,51 @@ class LidarFieldEngine:
         """[3, N, 3] tensor (rays_o | rays_d | gt), device or pinned host memory -> static buffers, one async copy."""
         self.batch.copy_(batch, non_blocking=True)
 
+    @torch.no_grad()
+    def render(self, rays_o, rays_d, perturb=False):
+        """Forward only, for evaluation: occupancy march (no jitter by default) -> field -> compositing of `rays_o/rays_d`
+        [n,3] (any n; processed in chunks of the engine's ray count) with the CURRENT parameters and occupancy grid.
+        Returns (weights_sum [n], absolute depth [n], image [n,2]) - what `NeRFRenderer.render` returns for the LiDAR
+        branch (renderer.py:268-297)."""
+        self.flush()
+        c = self.cfg
+        n = rays_o.shape[0]
+        ws, depth, image = (torch.empty(n, device=self.dev), torch.empty(n, device=self.dev),
+                            torch.empty(n, 2, device=self.dev))
+        keep = (c.perturb, self.rays_o.clone(), self.rays_d.clone())
+        c.perturb = bool(perturb)
+        try:
+            for lo in range(0, n, self.N):
+                hi = min(lo + self.N, n)
+                k = hi - lo
+                self.rays_o[:k].copy_(rays_o[lo:hi])
+                self.rays_d[:k].copy_(rays_d[lo:hi])
+                if k < self.N:                       # pad the last chunk with copies of its first ray
+                    self.rays_o[k:].copy_(rays_o[lo:lo + 1].expand(self.N - k, 3))
+                    self.rays_d[k:].copy_(rays_d[lo:lo + 1].expand(self.N - k, 3))
+                self._fb_march()
+                if c.fused_composite:                # (t0 is otherwise produced by the fused compositing kernel)
+                    torch.clamp(self.nears * c.dt_gamma, float(self.dt_min), float(self.dt_max), out=self.t0)
+                    torch.addcmul(self.nears, self.t0, self.noises, out=self.t0)
+                self._fwd_field()
+                self.composite_forward()
+                ws[lo:hi] = self.ws[:k]
+                depth[lo:hi] = torch.addcmul(self.depth, self.t0, self.ws)[:k]
+                image[lo:hi] = self.image[:k]
+        finally:
+            c.perturb = keep[0]
+            self.rays_o.copy_(keep[1])
+            self.rays_d.copy_(keep[2])
+        return ws, depth, image
+
+    def set_batch_from_pixels(self, pose, inds, image, H, W, fov_up, fov):
+        """The reference's per-step collate on the device (kitti360_dataset.py:123-159): `pose` [4,4] fp32 (lidar2world,
+        already offset/scaled), `inds` [N] int32 flat pixel indices, `image` [H*W, 3] fp32 (ray-drop, intensity,
+        depth * scale) of a frame resident on the device -> rays_o / rays_d / gt in the static buffers, one kernel."""
+        _ck(lib.lnb_lidar_batch(vp(pose.data_ptr()), vp(inds.data_ptr()), vp(image.data_ptr()), u32(self.N), u32(H), u32(W),
+                                f32(fov_up), f32(fov), vp(self.rays_o.data_ptr()), vp(self.rays_d.data_ptr()),
+                                vp(self.gt.data_ptr()), self._s()), "lidar_batch")
+
     def train_step(self, use_graph=True):
         """One optimiser step on the batch currently in the static buffers.  In graph mode on one rank the update is
         applied at the START of the next step (next to its march) - call flush() before reading parameters."""

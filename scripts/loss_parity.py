@@ -1,9 +1,11 @@
 """Loss parity at matched quality (BASELINE.json: ">= 10x ... at matched depth/intensity loss").
 
 Trains BASELINE config 2 (synthetic 64x1024 sequence, hash grid L16 F2 T2^19 + two 64x2 MLPs, 4096 rays/step, Adam
-lr 1e-2) on the SAME frames with the SAME loss in three ways and evaluates every parameter set with ONE evaluator - the
-reference-semantic dense renderer `NeRFRenderer.run` (768 + 64 samples, no jitter; renderer.py:99-298) - on HELD-OUT
-frames of the sequence:
+lr 1e-2) on the SAME frames with the SAME loss in three ways and evaluates each on HELD-OUT frames of the sequence with the
+renderer it was trained with - the dense variant with the reference-semantic `NeRFRenderer.run` (768 + 64 samples, no
+jitter; renderer.py:99-298), the engine with its occupancy march (no jitter); the engine's parameters are ALSO put through
+the dense evaluator (`dense_evaluator`), which ignores the occupancy grid and therefore sees the never-trained space
+behind / between the occupied cells:
 
   (i)   dense      the reference's sampling: render() -> dense `run` 768 + 64 (per-op sm_100a kernels + torch autograd,
                    GradScaler, torch Adam) - what the unmodified reference trains with (configs/kitti360_1908.txt:9-10);
@@ -64,6 +66,26 @@ def evaluate(net, seq, emb, w_sigma, w_head):
         m = gt[:, 0]
         depth = out["depth_lidar"][0].float()
         img = out["image_lidar"][0].float()
+        d_l1 += float(((depth - gt[:, 2]).abs() * m).sum()) / seq.scale
+        i_mse += float((((img[:, 1] - gt[:, 1]) ** 2) * m).sum())
+        r_mse += float(((img[:, 0] - m) ** 2).sum())
+        n_valid += float(m.sum())
+        n_all += m.numel()
+    return {"depth_l1_m": d_l1 / n_valid, "intensity_mse": i_mse / n_valid, "raydrop_mse": r_mse / n_all}
+
+
+@torch.no_grad()
+def evaluate_march(eng, seq):
+    """Held-out frames through the engine's OWN renderer (occupancy march without jitter, current grid)."""
+    d_l1, i_mse, r_mse, n_valid, n_all = 0.0, 0.0, 0.0, 0.0, 0
+    dirs_s = lidar_directions(seq.H, seq.W, seq.fov_up, seq.fov, dev)
+    for f in HELD:
+        pose = seq.poses[f]
+        rd = (dirs_s @ pose[:3, :3].T).contiguous()
+        ro = pose[:3, 3].expand_as(rd).contiguous()
+        gt = seq.images[f]
+        _, depth, img = eng.render(ro, rd)
+        m = gt[:, 0]
         d_l1 += float(((depth - gt[:, 2]).abs() * m).sum()) / seq.scale
         i_mse += float((((img[:, 1] - gt[:, 1]) ** 2) * m).sum())
         r_mse += float(((img[:, 0] - m) ** 2).sum())
@@ -143,7 +165,8 @@ def train_engine(seq, evalnet, steps, max_steps):
             torch.cuda.synchronize()
         if it in CHECK:
             eng.flush()
-            res[it] = evaluate(evalnet, seq, *split(eng))
+            res[it] = evaluate_march(eng, seq)                           # the renderer a user of this engine gets
+            res[it]["dense_evaluator"] = evaluate(evalnet, seq, *split(eng))   # (ignores the occupancy grid)
             res[it]["train_loss"] = eng.read_loss() / max(1, it - max([0] + [c for c in CHECK if c < it]))
             spr = eng.samples_last_step()[0] / N
             res[it]["samples_per_ray"] = spr

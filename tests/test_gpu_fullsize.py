@@ -185,3 +185,14 @@ def test_adam_keeps_the_fp16_shadow_in_sync_at_full_size(full):
     assert moved > 0.01, "parameters addressed by the batch must move"
     # first Adam step: |delta| <= lr for every parameter (bias-corrected m/sqrt(v) = +-1)
     assert float((eng.P - p0).abs().max()) <= eng.cfg.lr * 1.001
+
+
+def test_full_size_step_matches_cpu_restatement_at_4096_rays():
+    """BASELINE config 2 at full size - 4096 rays, the 2^19-entry table (13.7 M parameters), max_steps 1024, clumpy
+    occupancy grid: ONE fused step (loss, per-ray outputs, per-ray sample counts, every gradient) against the CPU
+    restatement.  (The restatement takes ~20 s on the host cores for this size.)"""
+    from oracle import check_engine
+    cfg = check_engine.small_config(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024)
+    eng, gpu, cpu = check_engine.run_pair(n_rays=4096, device=DEV, cfg=cfg, seed=2, fill=0.05)
+    assert eng.n_params == 13693520 and gpu["n_samples"] > 100000
+    check_engine.compare(gpu, cpu, eng.n_table)
