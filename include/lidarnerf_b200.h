@@ -67,6 +67,10 @@ int lnb_morton3D_invert(const int32_t *indices, uint32_t N, int32_t *coords, lnb
 /* raymarching.cu:308-320  grid [N*8] fp32 -> bitfield [N] u8, bit i = grid[8n+i] > thresh */
 int lnb_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *bitfield,
                  lnb_stream_t stream);
+/* packbits with the threshold min(*mean_density_dev, density_thresh_cap) read on the device (the occupancy-grid rule
+ * density_thresh = min(mean_density, density_thresh) of SURVEY.md Appendix A without a host round trip) */
+int lnb_packbits_dev(const float *grid, uint32_t N, const float *mean_density_dev, float density_thresh_cap,
+                     uint8_t *bitfield, lnb_stream_t stream);
 
 /* raymarching.cu:536-568.  counter[0] += samples, counter[1] += rays (device atomics);
  * rays [N,3] = (ray id, sample offset, sample count) in arrival order; samples of a ray whose

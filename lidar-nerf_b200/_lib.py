@@ -51,7 +51,7 @@ SYMBOLS = [
     "lnb_pano_to_lidar_workspace_bytes", "lnb_pano_to_lidar",
     "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
     "lnb_field_fused_weight_bytes", "lnb_field_pack_weights", "lnb_field_fused_forward",
-    "lnb_lidar_loss_ex", "lnb_lidar_composite_forward", "lnb_lidar_composite_backward", "lnb_dp_adam_exchange_mc", "lnb_lidar_batch",
+    "lnb_lidar_loss_ex", "lnb_lidar_composite_forward", "lnb_lidar_composite_backward", "lnb_dp_adam_exchange_mc", "lnb_lidar_batch", "lnb_packbits_dev",
 ]
 
 

@@ -128,6 +128,28 @@ k_packbits(const float4 *__restrict__ grid, uint32_t N, float thresh, uint8_t *_
     bits[n] = (uint8_t)v;
 }
 
+// The same with the threshold read from device memory, thresh = min(*mean, cap): the density-grid refresh of the training
+// engine computes the grid mean on the device and never synchronises with the host (nerf/engine.py).
+__global__ void __launch_bounds__(256)
+k_packbits_dev(const float4 *__restrict__ grid, uint32_t N, const float *__restrict__ mean, float cap,
+               uint8_t *__restrict__ bits) {
+    const uint32_t n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n >= N) return;
+    const float thresh = fminf(__ldg(mean), cap);
+    const float4 a = __ldg(grid + 2 * (size_t)n);
+    const float4 b = __ldg(grid + 2 * (size_t)n + 1);
+    unsigned v = 0;
+    v |= (a.x > thresh) ? 1u : 0u;
+    v |= (a.y > thresh) ? 2u : 0u;
+    v |= (a.z > thresh) ? 4u : 0u;
+    v |= (a.w > thresh) ? 8u : 0u;
+    v |= (b.x > thresh) ? 16u : 0u;
+    v |= (b.y > thresh) ? 32u : 0u;
+    v |= (b.z > thresh) ? 64u : 0u;
+    v |= (b.w > thresh) ? 128u : 0u;
+    bits[n] = (uint8_t)v;
+}
+
 // ------------------------------------------------------------------------------------------
 // warp-cooperative marcher
 // ------------------------------------------------------------------------------------------
@@ -954,6 +976,17 @@ int lnb_packbits(const float *grid, uint32_t N, float density_thresh, uint8_t *b
     if (N == 0) return LNB_OK;
     k_packbits<<<blocks_for_threads(N, 256), 256, 0, as_stream(stream)>>>(
         reinterpret_cast<const float4 *>(grid), N, density_thresh, bitfield);
+    count_launch();
+    return launch_status();
+}
+
+int lnb_packbits_dev(const float *grid, uint32_t N, const float *mean_density_dev, float density_thresh_cap,
+                     uint8_t *bitfield, lnb_stream_t stream) {
+    LNB_REQUIRE(grid && bitfield && mean_density_dev);
+    LNB_REQUIRE((reinterpret_cast<uintptr_t>(grid) & 15u) == 0);
+    if (N == 0) return LNB_OK;
+    k_packbits_dev<<<blocks_for_threads(N, 256), 256, 0, as_stream(stream)>>>(
+        reinterpret_cast<const float4 *>(grid), N, mean_density_dev, density_thresh_cap, bitfield);
     count_launch();
     return launch_status();
 }

@@ -21,6 +21,7 @@ The step, in launch order:
 """
 import ctypes as C
 import math
+import os
 
 import numpy as np
 import torch
@@ -738,35 +739,74 @@ class LidarFieldEngine:
     @torch.no_grad()
     def update_density_grid(self, decay=0.95, full=None):
         """EMA-max refresh of the density grid from the current network + packbits, merged
-        with the LiDAR prior grid (cells a GT return falls into stay occupied)."""
+        with the LiDAR prior grid (cells a GT return falls into stay occupied).  The first 16 refreshes visit every
+        cell; the steady-state partial refresh (H^3/4 uniform + H^3/4 occupied cells per cascade) runs WITHOUT any host
+        synchronisation and is replayed as one CUDA graph."""
         from ..raymarching import packbits
         c = self.cfg
         if self.ex.world > 1:
             torch.cuda.current_stream().wait_stream(self._comm)   # the network is evaluated: parameters must be settled
-        H3 = c.grid_size ** 3
         n_updates = self.step_count // max(c.grid_update_interval, 1)
         full = (n_updates <= 16) if full is None else full
+        if not full:
+            return self._refresh_partial(decay)
         for cas in range(c.cascade):
-            if full:
-                sig = self.query_density(self.cell_centers(cas))
-                self.density_grid[cas] = torch.maximum(self.density_grid[cas] * decay, sig)
-            else:   # H^3/4 uniform random cells + H^3/4 currently occupied cells
-                nq = H3 // 4
-                rnd = torch.randint(0, H3, (nq,), device=self.dev)
-                occ = torch.nonzero(torch.maximum(self.density_grid[cas], self.prior_grid[cas]) > 0).squeeze(-1)
-                if occ.numel() > 0:
-                    occ = occ[torch.randint(0, occ.numel(), (nq,), device=self.dev)]
-                    sel = torch.cat([rnd, occ])
-                else:
-                    sel = rnd
-                sig = self.query_density(self.cell_centers(cas, sel))
-                cur = self.density_grid[cas]
-                # duplicates in `sel` resolve to one of the candidate values, like torch-ngp's indexed assignment
-                cur[sel] = torch.maximum(cur[sel] * decay, sig)
+            sig = self.query_density(self.cell_centers(cas))
+            self.density_grid[cas] = torch.maximum(self.density_grid[cas] * decay, sig)
         merged = torch.maximum(self.density_grid, self.prior_grid)
         self.mean_density = float(merged.clamp(min=0).mean().item())
         thresh = min(self.mean_density, c.density_thresh)
         packbits(merged, thresh, self.bitfield)
+
+    def _refresh_partial_body(self, decay):
+        """Partial refresh, device-only: per cascade H^3/4 uniformly random cells + H^3/4 cells drawn uniformly from the
+        currently occupied ones (the k-th occupied cell via a prefix sum of the occupancy mask + binary search instead of
+        torch.nonzero, whose result size would have to travel to the host), re-evaluated with the current network."""
+        c = self.cfg
+        H3 = c.grid_size ** 3
+        nq = H3 // 4
+        dev = self.dev
+        for cas in range(c.cascade):
+            cur = self.density_grid[cas]
+            mask = torch.maximum(cur, self.prior_grid[cas]) > 0
+            cs = torch.cumsum(mask, 0, dtype=torch.int32)
+            total = cs[-1:]
+            rnd = torch.randint(0, H3, (nq,), device=dev)
+            k = (torch.rand(nq, device=dev) * total).to(torch.int32)
+            k = torch.minimum(k, torch.clamp(total - 1, min=0))
+            occ = torch.searchsorted(cs, k + 1)
+            occ = torch.where(total > 0, occ, rnd).clamp_(max=H3 - 1)
+            sel = torch.cat([rnd, occ])
+            sig = self.query_density(self.cell_centers(cas, sel))
+            # duplicates in `sel` resolve to one of the candidate values, like torch-ngp's indexed assignment
+            cur[sel] = torch.maximum(cur[sel] * decay, sig)
+        merged = torch.maximum(self.density_grid, self.prior_grid)
+        self._mean_density_dev.copy_(merged.clamp_(min=0).mean().reshape(1))
+        _ck(lib.lnb_packbits_dev(vp(merged.data_ptr()), u32(merged.numel() // 8), vp(self._mean_density_dev.data_ptr()),
+                                 f32(c.density_thresh), vp(self.bitfield.data_ptr()), self._s()), "packbits_dev")
+
+    def _refresh_partial(self, decay):
+        if not hasattr(self, "_mean_density_dev"):
+            self._mean_density_dev = torch.zeros(1, dtype=torch.float32, device=self.dev)
+            self._refresh_graph = None
+            self._refresh_decay = None
+        if os.environ.get("LNB_REFRESH_GRAPH", "1") == "0":
+            return self._refresh_partial_body(decay)
+        if self._refresh_graph is None or self._refresh_decay != decay:
+            # warm up on a side stream (allocator, lazy loads), then capture; the refresh draws its random numbers
+            # through torch's graph-safe generator state
+            side = torch.cuda.Stream(device=self.dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self._refresh_partial_body(decay)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize(self.dev)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, capture_error_mode="thread_local"):
+                self._refresh_partial_body(decay)
+            self._refresh_graph, self._refresh_decay = g, decay
+            return                               # (the warm-up run above was this call's refresh)
+        self._refresh_graph.replay()
 
     @torch.no_grad()
     def seed_occupancy_from_points(self, points, dilate=1, value=1e4):
