@@ -323,12 +323,21 @@ def main():
     cursor = [0]
 
     def run(steps, host):
-        for _ in range(steps):
+        if host:
+            # end to end: every step's batch comes from PINNED HOST memory; the copy of batch i+1 is started (copy stream,
+            # double-buffered staging) right after step i has been launched, so it runs under that step's compute
+            eng.stage_batch(pool_host[cursor[0] % len(pool_host)])
+        for j in range(steps):
             i = cursor[0]
             cursor[0] += 1
-            load(pool_host[i % len(pool_host)] if host else pool[i % len(pool)])
+            if host:
+                eng.set_batch_staged()
+            else:
+                load(pool[i % len(pool)])
             eng.train_step(use_graph=not args.no_graph)
             if host:
+                if j + 1 < steps:
+                    eng.stage_batch(pool_host[(i + 1) % len(pool_host)])
                 # D2H read of the step's loss, every step: copied to pinned memory behind the step and consumed on the
                 # host one step later, so the launch queue never drains (the last one is collected after the loop)
                 losses.append(eng.read_loss_async())

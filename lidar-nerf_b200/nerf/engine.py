@@ -531,6 +531,36 @@ class LidarFieldEngine:
         """[3, N, 3] tensor (rays_o | rays_d | gt), device or pinned host memory -> static buffers, one async copy."""
         self.batch.copy_(batch, non_blocking=True)
 
+    # ---- host batches: double-buffered staging so that the H2D copy of step i+1 runs under the compute of step i --------
+    def stage_batch(self, host_batch):
+        """Start the asynchronous copy of a pinned host batch [3, N, 3] (rays_o | rays_d | gt) into the next staging slot
+        on the engine's copy stream.  Pair with `set_batch_staged()`; call it for batch i+1 right after launching step i."""
+        if not hasattr(self, "_stage"):
+            self._stage = [torch.empty_like(self.batch) for _ in range(2)]
+            self._stage_ready = [torch.cuda.Event(), torch.cuda.Event()]
+            self._stage_free = [None, None]
+            self._copy_stream = torch.cuda.Stream(device=self.dev)
+            self._stage_w = 0
+            self._stage_r = 0
+        k = self._stage_w & 1
+        with torch.cuda.stream(self._copy_stream):
+            if self._stage_free[k] is not None:
+                self._copy_stream.wait_event(self._stage_free[k])      # the step that read this slot has consumed it
+            self._stage[k].copy_(host_batch, non_blocking=True)
+            self._stage_ready[k].record(self._copy_stream)
+        self._stage_w += 1
+
+    def set_batch_staged(self):
+        """Main stream: wait for the oldest staged batch and move it (device to device, 147 KB) into the static buffers."""
+        k = self._stage_r & 1
+        main = torch.cuda.current_stream()
+        main.wait_event(self._stage_ready[k])
+        self.batch.copy_(self._stage[k], non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(main)
+        self._stage_free[k] = ev
+        self._stage_r += 1
+
     @torch.no_grad()
     def render(self, rays_o, rays_d, perturb=False):
         """Forward only, for evaluation: occupancy march (no jitter by default) -> field -> compositing of `rays_o/rays_d`

@@ -21,6 +21,7 @@ def run_pair(n_rays=256, device="cuda:0", cfg=None, seed=0, fill=0.2, patch_smoo
     from lidar_nerf_b200.nerf.engine import LidarFieldEngine
     cfg = cfg or small_config()
     rng = np.random.default_rng(seed)
+    torch.manual_seed(4321 + seed)          # the march jitter is drawn from torch's generator: reproducible inputs
     eng = LidarFieldEngine(cfg, n_rays, device=device, sample_budget=n_rays * 96)
     # rays from a point near the origin, random directions; random ground truth
     rays_o = np.tile(rng.uniform(-0.02, 0.02, size=(1, 3)), (n_rays, 1)).astype(np.float32)

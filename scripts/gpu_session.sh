@@ -42,14 +42,14 @@ if has ref; then
 fi
 if has launches; then
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off -c 400 --csv --log-file $OUT/launches.csv \
-    python bench.py --steps 3 --warmup 200 --no-graph --no-cpu-baseline --no-profile --profiler-range > $OUT/launches_bench.log 2>&1
+    python bench.py --steps 3 --warmup 320 --no-graph --no-cpu-baseline --no-profile --no-api-b2 --no-reference-cuda --profiler-range > $OUT/launches_bench.log 2>&1
   echo "launch list rows: $(wc -l < $OUT/launches.csv)"
 fi
 if has full; then
   # the heavy kernels of one steady-state step (eager launches; skip the preparation phase's launches)
   timeout 900 ncu --set full --clock-control none --import-source on \
-    -k regex:'k_field_fwd|k_mlp_bwd|k_grid_fwd|k_grid_bwd|k_march_train|k_adam|k_composite_train|k_lidar_composite_step|k_ray_dir_terms' \
+    -k regex:'k_field_fused_fwd|k_field_fwd|k_mlp_bwd|k_grid_fwd|k_grid_bwd|k_march_train|k_adam|k_composite_train|k_lidar_composite_step|k_ray_dir_terms|k_pack_field_weights' \
     --profile-from-start off -c ${NCU_COUNT:-12} -f -o $OUT/full \
-    python bench.py --steps 2 --warmup 200 --no-graph --no-cpu-baseline --no-profile --profiler-range > $OUT/full_bench.log 2>&1
+    python bench.py --steps 2 --warmup 320 --no-graph --no-cpu-baseline --no-profile --no-api-b2 --no-reference-cuda --profiler-range > $OUT/full_bench.log 2>&1
   ls -la $OUT/full.ncu-rep
 fi
