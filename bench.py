@@ -471,7 +471,9 @@ def main():
                "e2e": {"value": world * N * args.steps / (ms_e2e * 1e-3), "unit": "rays/s",
                        "h2d_bytes_per_step": N * 9 * 4, "d2h_bytes_per_step": 4,
                        "loss_readback": "every step: 4 B D2H into pinned memory behind the step, consumed on the host "
-                                        "one step later (no queue drain)",
+                                        "three steps later (no queue drain)",
+                       "batch_upload": "every step: 147 KB H2D from pinned memory on a copy stream into a double-buffered "
+                                       "staging slot, started when the previous step is launched",
                        "last_loss": next((x for x in reversed(losses) if x is not None), None)},
                "gpu_launches": int(round(launches))}
         if roof:

@@ -695,30 +695,37 @@ class LidarFieldEngine:
             self._alloc_samples(want)
         return self.M
 
+    LOSS_RING = 4
+
     def read_loss_async(self):
         """Device->host read of the step's loss without draining the launch queue: the 4 bytes are copied into pinned
-        memory behind the step (stream-ordered) and the accumulator is cleared; returns the loss copied by the PREVIOUS
-        call (None the first time), which has long arrived.  `read_loss_last()` collects the final one."""
+        memory behind the step (stream-ordered) and the accumulator is cleared; returns the loss copied LOSS_RING - 1
+        calls ago (None until then), which has long arrived - the host never waits for the step it has just launched and
+        stays a few steps ahead of the device.  `read_loss_last()` collects the newest one."""
+        R = self.LOSS_RING
         if not hasattr(self, "_loss_pin"):
-            self._loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(2)]
-            self._loss_ev = [None, None]
+            self._loss_pin = [torch.zeros(1, dtype=torch.float32).pin_memory() for _ in range(R)]
+            self._loss_ev = [None] * R
             self._loss_slot = 0
         k = self._loss_slot
+        old_ev = self._loss_ev[k]
+        old = None
+        if old_ev is not None:          # the slot about to be overwritten holds the loss of R calls ago: hand it out
+            old_ev.synchronize()
+            old = float(self._loss_pin[k][0])
         self._loss_pin[k].copy_(self.loss_acc, non_blocking=True)
         self.loss_acc.zero_()
         ev = torch.cuda.Event()
         ev.record()
         self._loss_ev[k] = ev
-        self._loss_slot = k ^ 1
-        prev = self._loss_ev[k ^ 1]
-        if prev is None:
-            return None
-        prev.synchronize()
-        return float(self._loss_pin[k ^ 1][0])
+        self._loss_slot = (k + 1) % R
+        return old
 
     def read_loss_last(self):
-        k = self._loss_slot ^ 1
-        if not hasattr(self, "_loss_pin") or self._loss_ev[k] is None:
+        if not hasattr(self, "_loss_pin"):
+            return None
+        k = (self._loss_slot - 1) % self.LOSS_RING
+        if self._loss_ev[k] is None:
             return None
         self._loss_ev[k].synchronize()
         return float(self._loss_pin[k][0])
