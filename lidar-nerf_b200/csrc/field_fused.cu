@@ -1,25 +1,31 @@
 // One persistent kernel per ray packet: hash-grid gather -> density MLP -> LiDAR head (forward).
 //
-// What the two-kernel forward (k_grid_fwd -> enc [M,32] in HBM -> k_field_fwd) did in sequence - an L1/L2-gather-bound
+// What the two-kernel forward (k_grid_fwd -> enc [M,32] in HBM -> k_field_fwd) does in sequence - an L1/L2-gather-bound
 // kernel followed by a latency-bound tensor-core kernel, each owning the whole SM while the other's units idle - runs
-// here concurrently inside ONE CTA per SM, warp-specialised:
+// here concurrently inside ONE CTA per SM (800 threads), warp-specialised:
 //
-//   warps  0..15  GATHER     warp <-> level (32 neighbouring samples per gather instruction, all 8 corner loads of a
-//                            sample in flight), results written as fp16 pairs STRAIGHT INTO the swizzled shared-memory
-//                            operand tile of the first MLP layer (a ring of kStages tiles, full/empty mbarriers);
-//   warps 16..23  EPILOGUE   two groups of 128 threads (thread = tile row), one 128-row tile in flight each:
-//                            tcgen05.ld accumulator row -> (+per-ray bias) -> ReLU -> fp16 -> operand tile of the next
-//                            layer (+ the saved activation row to HBM straight from registers); sigma = exp(h0), geo
-//                            features -> head operand; sigmoid -> (ray-drop, intensity);
+//   warps  0..15  GATHER     warp <-> level (32 neighbouring samples per gather instruction, the 8 corner rows of TWO
+//                            sample groups = 16 loads per lane in flight), results written as fp16 pairs STRAIGHT INTO
+//                            the swizzled shared-memory operand tile of the first MLP layer (a ring of kStages tiles,
+//                            full/empty mbarriers; coordinates double-buffered in shared memory);
+//   warps 16..23  EPILOGUE   two groups of 128 threads (thread = tile row = TMEM lane), one 128-row tile in flight each:
+//                            tcgen05.ld accumulator row, 32 columns at a time -> (+per-ray bias) -> ReLU -> fp16 ->
+//                            operand tile of the next layer; the saved activations leave the SM as warp-local coalesced
+//                            512-byte stores read back from that tile while the tensor core works; sigma = exp(h0),
+//                            geo features -> head operand; sigmoid -> (ray-drop, intensity); one mbarrier arrival per
+//                            WARP (fence.proxy.async by every lane, __syncwarp, lane 0 arrives);
 //   warp   24     MMA        one elected lane issues every tcgen05.mma of the CTA (M128 x N64/N16 x K16, fp32
-//                            accumulators in tensor memory, 128 columns per group), polling the groups' mbarriers.
+//                            accumulators in tensor memory, 128 columns per tile slot), polling the slots' mbarriers
+//                            and consuming the operand ring strictly in tile order.
 //
 // MLP weights are staged ONCE per CTA by the TMA engine: `lnb_field_pack_weights` lays the six weight tiles out in global
 // memory as the exact shared-memory image (128-byte rows, 16-byte chunks xor-swizzled) and the kernel pulls that image
 // with cp.async.bulk (SASS UBLKCP) onto an mbarrier - no per-thread LDGSTS, no register staging.
 //
 // Numerics are those of k_grid_fwd + k_field_fwd (same helpers, same rounding points): tests compare the two paths
-// bit-for-bit on the saved activations.
+// bit-for-bit on everything the step keeps.  Measured (profiles/r02_fused_forward_diag.txt): at 385 k samples 164 us vs
+// 97 + 72 us for the two kernels - the overlap is real but each role only has a share of the SM's warps and registers
+// (gather alone 136 us with 16 warps vs 97 us with 48; MLP alone 99 us vs 72 us), so the gain over the sequence is small.
 //
 // Reference behaviour: gridencoder.cu:95-199 (gather), ffmlp.cu:460-576 (MLP), network.py:162-237 (wiring).
 #include <cstdlib>

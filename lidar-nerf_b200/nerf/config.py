@@ -56,8 +56,9 @@ class FieldConfig:
     late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam
     fused_exchange: bool = True          # data parallel: one peer-memory kernel (reduce-scatter + Adam + all-gather) over
                                          # NVLink via torch symmetric memory; falls back to NCCL when it cannot be set up
-    multicast_exchange: bool = True      # ... through NVSwitch multicast / in-switch reduction (multimem.ld_reduce / .st) when
-                                         # the symmetric-memory handle exposes multicast addresses (NVLS)
+    multicast_exchange: bool = False     # ... through NVSwitch multicast / in-switch reduction (multimem.ld_reduce / .st, NVLS)
+                                         # instead of peer loads/stores.  Correct (2-GPU test) but measured SLOWER on B200:
+                                         # 0.741 vs 0.651 ms/step at 2 GPUs, 0.849 vs 0.812 at 8 (profiles/r02_summary.md)
     overlap_exchange: bool = True        # data parallel, graph mode: the exchange overlaps the next step's march
     pipeline_adam: bool = False          # graph mode, one rank: Adam of step i runs next to the march of step i+1
                                          # (measured: -6 us/step device time, +CPU launch work; off by default)
