@@ -239,47 +239,17 @@ k_grid_bwd(const TG *__restrict__ grad, const float *__restrict__ inputs,
     const bool has_grad = in_range && inside;
     const size_t g_stride = (layout == LNB_LAYOUT_LBC) ? (size_t)B * C : (size_t)C;
     const TG *gp = (layout == LNB_LAYOUT_LBC) ? grad + (size_t)b * C : grad + (size_t)b * L * C;
-    // Staged gradient rows ([B, L*C] layout, 16-bit gradients, C = 2, rows of whole 16-byte chunks): each thread pulls its
-    // row with 16-byte loads (every fetched sector is used; the per-level 4-byte loads at a 64-byte lane stride fetched
-    // each sector twice and put a dependent global load in front of every level - 25 % of the kernel's stall samples) and
-    // parks it in shared memory as [level][thread] words, conflict-free for the per-level reads below.
-    constexpr bool kCanStage = sizeof(TG) == 2 && C == 2;
-    __shared__ uint32_t s_grow[kCanStage ? 16 * kBwdThreads : 1];
-    const bool staged = kCanStage && layout == LNB_LAYOUT_BLC && L <= 16 && (L % 4) == 0;
     float gv_next[C];
 #pragma unroll
     for (uint32_t c = 0; c < C; ++c) gv_next[c] = 0.f;
-    if (staged) {
-        if constexpr (kCanStage) {
-            if (has_grad) {
-                const uint4 *row = reinterpret_cast<const uint4 *>(gp);
-                for (uint32_t q = 0; q < L / 4; ++q) {
-                    const uint4 w = __ldg(row + q);
-                    s_grow[(4 * q + 0) * kBwdThreads + threadIdx.x] = w.x;
-                    s_grow[(4 * q + 1) * kBwdThreads + threadIdx.x] = w.y;
-                    s_grow[(4 * q + 2) * kBwdThreads + threadIdx.x] = w.z;
-                    s_grow[(4 * q + 3) * kBwdThreads + threadIdx.x] = w.w;
-                }
-            }
-        }
-    } else if (has_grad) {
-        load_grad_row<TG, C>(gp, gv_next);
-    }
+    if (has_grad) load_grad_row<TG, C>(gp, gv_next);
     __syncthreads();
 
     for (uint32_t level = 0; level < L; ++level) {
         float gv[C];
-        if (staged) {
-            if constexpr (kCanStage) {
-                const uint32_t w = has_grad ? s_grow[level * kBwdThreads + threadIdx.x] : 0u;
-                const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&w));
-                gv[0] = f.x, gv[1] = f.y;
-            }
-        } else {
 #pragma unroll
-            for (uint32_t c = 0; c < C; ++c) gv[c] = gv_next[c];
-            if (has_grad && level + 1 < L) load_grad_row<TG, C>(gp + (size_t)(level + 1) * g_stride, gv_next);   // one level ahead
-        }
+        for (uint32_t c = 0; c < C; ++c) gv[c] = gv_next[c];
+        if (has_grad && level + 1 < L) load_grad_row<TG, C>(gp + (size_t)(level + 1) * g_stride, gv_next);   // one level ahead
 
         LevelGeo g;
         LevelIndex<D> li;

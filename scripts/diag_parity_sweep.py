@@ -8,8 +8,13 @@ import torch
 from oracle import check_engine
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 16
+patch = "patch" in sys.argv[2:]
 for seed in range(n):
-    eng, gpu, cpu = check_engine.run_pair(n_rays=256, device="cuda:0", seed=seed)
+    if patch:
+        eng, gpu, cpu = check_engine.run_pair(n_rays=256, device="cuda:0", seed=seed, patch_smooth_gt=True,
+                                              cfg=check_engine.small_config(patch_size=(2, 8), alpha_grad=100.0))
+    else:
+        eng, gpu, cpu = check_engine.run_pair(n_rays=256, device="cuda:0", seed=seed)
     a, b = gpu["grad"].astype(np.float64), cpu["grad"].astype(np.float64)
     nt = eng.n_table
     rel_t = np.linalg.norm(a[:nt] - b[:nt]) / np.linalg.norm(b[:nt])
