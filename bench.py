@@ -31,7 +31,7 @@ RAYS = 4096
 #   4  configs[3]: NeRF-MVL-like object scan - 256 x 1800 pano, fov (15, 40) deg, scale 0.005 (configs/nerf_mvl.txt),
 #      spherical-harmonics (degree 4) direction encoding in the head, alpha_i = 1, bound 1, occupancy march.
 #   5  configs[4]: large-bound scene - bound 4 (cascade 3, 768 KiB bitfield), max_steps 128, 16384 rays per GPU and step
-#      (the 8-GPU roofline sweep; the MLPs run in fp16 on the tensor cores with fp32 accumulation - see DESIGN.md on bf16).
+#      with the MLPs in bf16 on the tensor cores (`_bf16` builds of the kernels, fp32 accumulation) - the 8-GPU roofline sweep.
 WORKLOADS = {
     2: dict(rays=4096, field={}, seq={}, text=WORKLOAD),
     4: dict(rays=4096, field=dict(dir_encoding="sh", sh_degree=4, min_near_lidar=0.005, alpha_i=1.0),
@@ -39,10 +39,10 @@ WORKLOADS = {
             text=("NeRF-MVL-like synthetic 256x1800 pano x 8 frames (fov 15/40 deg, scale 0.005), hashgrid L16 F2 T2^19 "
                   "res16->32768 + ffmlp 64x2 sigma + ffmlp 64x2 head with SH(4) direction encoding, 4096 rays/GPU/step, "
                   "occupancy march max_steps=1024 dt_gamma=0, fwd+bwd+Adam+grid refresh/16 steps")),
-    5: dict(rays=16384, field=dict(bound=4.0, max_steps=128, min_near_lidar=4.0 / 92.7),
+    5: dict(rays=16384, field=dict(bound=4.0, max_steps=128, min_near_lidar=4.0 / 92.7, mlp_dtype="bf16"),
             seq=dict(scale=4.0 / 92.7),
             text=("large-bound synthetic 64x1024 pano x 8 frames, bound 4 (cascade 3), hashgrid L16 F2 T2^19 res16->32768 + "
-                  "ffmlp 64x2 sigma + ffmlp 64x2 lidar head, 16384 rays/GPU/step, occupancy march max_steps=128 dt_gamma=0, "
+                  "ffmlp 64x2 sigma + ffmlp 64x2 lidar head with bf16 MLPs on the tensor cores, 16384 rays/GPU/step, occupancy march max_steps=128 dt_gamma=0, "
                   "fwd+bwd+Adam+grid refresh/16 steps")),
 }
 
@@ -449,7 +449,9 @@ def main():
         value = world * N * args.steps / (ms * 1e-3)
         out = {"metric": WORKLOADS[args.config].get("metric", METRIC), "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
-               "vs_baseline": None, "dtype": "f16 tables+MLP (fp32 accumulate) / f32 march+composite+Adam",
+               "vs_baseline": None,
+               "dtype": ("f16 table + bf16 MLP (fp32 accumulate) / f32 march+composite+Adam" if cfg.mlp_dtype == "bf16" else
+                         "f16 tables+MLP (fp32 accumulate) / f32 march+composite+Adam"),
                "data": "synthetic",
                "config": bench_config(args.config),
                "detail": {"rays_per_gpu": N, "samples_per_step": produced, "samples_per_ray": produced / N,

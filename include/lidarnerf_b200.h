@@ -480,6 +480,64 @@ size_t lnb_pano_to_lidar_workspace_bytes(uint32_t H, uint32_t W);
 int lnb_pano_to_lidar(const float *pano, const float *intensities, uint32_t H, uint32_t W, float fov_up, float fov,
                       float *points_out, int32_t *count_out, void *workspace, lnb_stream_t stream);
 
+
+/* ------------------------------------------------------------------------------------------
+ * bf16 builds of the tensor-core MLP entry points (BASELINE config 5: "bf16 MLP on tensor cores"): identical signatures
+ * and semantics, but weights, activations, saved activations, sig_out / ray_enc rows and activation gradients are
+ * bfloat16 (tcgen05 kind::f16 with bf16 operand formats, fp32 accumulation).  The hash table stays fp16 (the persistent
+ * forward kernel converts the interpolated features) and the input gradient the density MLP hands to the hash-grid
+ * scatter stays fp16.  Same translation units compiled with -DLNB_BF16 (lidar-nerf_b200/build.py).
+ * ---------------------------------------------------------------------------------------- */
+int lnb_field_supported_bf16(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                        uint32_t degree, uint32_t hidden);
+int lnb_field_ray_terms_bf16(const float *rays_d, const void *w_head, uint32_t N, uint32_t degree, uint32_t in_pad,
+                        void *ray_enc, float *ray_bias, lnb_stream_t stream);
+int lnb_field_forward_bf16(const void *enc, const void *w_sigma, const void *w_head, const int32_t *ray_ids,
+                      const float *ray_bias, uint32_t M, uint32_t enc_dim, uint32_t sigma_layers,
+                      uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                      float density_scale, void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                      const int32_t *n_active, lnb_stream_t stream);
+int lnb_field_head_backward_bf16(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                            const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                            uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
+                            float density_scale, void *g_sig_out, float *grad_w_head_f32, const int32_t *n_active,
+                            lnb_stream_t stream);
+int lnb_field_head_backward_rows_bf16(const float *g_rgb, const float *rgb, const float *g_sigma, const void *sig_out,
+                                 const int32_t *ray_ids, const void *ray_enc, const void *w_head, const void *fb_head,
+                                 uint32_t M, uint32_t head_in_pad, uint32_t head_layers, uint32_t degree,
+                                 uint32_t hidden, float density_scale, void *g_sig_out, float *grad_w_head_f32,
+                                 const int32_t *row_idx, const int32_t *n_rows, lnb_stream_t stream);
+size_t lnb_field_fused_weight_bytes_bf16(uint32_t enc_dim, uint32_t sigma_layers, uint32_t head_in_pad, uint32_t head_layers,
+                                    uint32_t degree, uint32_t hidden);
+int lnb_field_pack_weights_bf16(const void *w_sigma, const void *w_head, uint32_t enc_dim, uint32_t sigma_layers,
+                           uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden, void *image,
+                           lnb_stream_t stream);
+int lnb_field_fused_forward_bf16(const float *xyzs, const void *table, const int32_t *offsets, uint32_t L, uint32_t C, float S,
+                            uint32_t H, float in_bound, const void *weight_image, const int32_t *ray_ids,
+                            const float *ray_bias, uint32_t M, uint32_t sigma_layers, uint32_t head_in_pad,
+                            uint32_t head_layers, uint32_t degree, uint32_t hidden, float density_scale, void *enc,
+                            void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
+                            const int32_t *n_active, lnb_stream_t stream);
+int lnb_ffmlp_forward_ex_bf16(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                         uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                         uint32_t output_activation, void *forward_buffer, void *outputs, const int32_t *n_active,
+                         lnb_stream_t stream);
+int lnb_ffmlp_inference_bf16(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,
+                        uint32_t output_dim, uint32_t hidden_dim, uint32_t num_layers,
+                        uint32_t activation, uint32_t output_activation, void *inference_buffer,
+                        void *outputs, lnb_stream_t stream);
+int lnb_ffmlp_backward_accumulate_bf16(const void *grad, const void *inputs, const void *weights,
+                                  const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                  uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                  uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
+                                  float *grad_weights_f32, const int32_t *n_active, lnb_stream_t stream);
+int lnb_ffmlp_backward_accumulate_rows_bf16(const void *grad, const void *inputs, const void *weights,
+                                       const void *forward_buffer, uint32_t B, uint32_t input_dim, uint32_t output_dim,
+                                       uint32_t hidden_dim, uint32_t num_layers, uint32_t activation,
+                                       uint32_t output_activation, int calc_grad_inputs, void *grad_inputs,
+                                       float *grad_weights_f32, const int32_t *row_idx, const int32_t *n_rows,
+                                       lnb_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -20,8 +20,9 @@ lib.lnb_strerror.restype = C.c_char_p
 lib.lnb_strerror.argtypes = [C.c_int]
 lib.lnb_arch.restype = C.c_char_p
 lib.lnb_launch_count.restype = C.c_uint64
-lib.lnb_field_fused_weight_bytes.restype = C.c_size_t
-lib.lnb_field_fused_weight_bytes.argtypes = [C.c_uint32] * 6
+for _n in ("lnb_field_fused_weight_bytes", "lnb_field_fused_weight_bytes_bf16"):
+    getattr(lib, _n).restype = C.c_size_t
+    getattr(lib, _n).argtypes = [C.c_uint32] * 6
 lib.lnb_ffmlp_backward_workspace_bytes.restype = C.c_size_t
 lib.lnb_ffmlp_backward_workspace_bytes.argtypes = [C.c_uint32] * 4
 for _n in ("lnb_lidar_to_pano_workspace_bytes", "lnb_pano_to_lidar_workspace_bytes"):
@@ -52,6 +53,7 @@ SYMBOLS = [
     "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
     "lnb_field_fused_weight_bytes", "lnb_field_pack_weights", "lnb_field_fused_forward",
     "lnb_lidar_loss_ex", "lnb_lidar_composite_forward", "lnb_lidar_composite_backward", "lnb_dp_adam_exchange_mc", "lnb_lidar_batch", "lnb_packbits_dev",
+    "lnb_field_supported_bf16", "lnb_field_ray_terms_bf16", "lnb_field_forward_bf16", "lnb_field_head_backward_bf16", "lnb_field_head_backward_rows_bf16", "lnb_field_fused_weight_bytes_bf16", "lnb_field_pack_weights_bf16", "lnb_field_fused_forward_bf16", "lnb_ffmlp_forward_ex_bf16", "lnb_ffmlp_inference_bf16", "lnb_ffmlp_backward_accumulate_bf16", "lnb_ffmlp_backward_accumulate_rows_bf16",
 ]
 
 

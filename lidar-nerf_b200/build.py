@@ -18,6 +18,8 @@ LIB_DIR = os.path.join(HERE, "lib")
 OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(LIB_DIR, "liblnb200.so")
 UNITS = ["raymarching", "gridencoder", "freqencoder", "shencoder", "ffmlp", "field", "field_fused", "optim", "fused", "pointcloud"]
+# the tensor-core MLP units are compiled a second time with bf16 operands (-DLNB_BF16, entry points `*_bf16`)
+BF16_UNITS = ["ffmlp", "field", "field_fused"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 
@@ -47,14 +49,17 @@ def build(force=False, verbose=False, trace=False):
     hdr = _newest_header()
     units = [u for u in UNITS if os.path.exists(os.path.join(CSRC, u + ".cu"))]
     todo = []
+    objs_all = []
     for u in units:
-        src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(OBJ_DIR, u + ".o")
-        if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr):
-            todo.append((u, src, obj))
+        for variant in (("", []), ("_bf16", ["-DLNB_BF16"])) if u in BF16_UNITS else (("", []),):
+            src, obj = os.path.join(CSRC, u + ".cu"), os.path.join(OBJ_DIR, u + variant[0] + ".o")
+            objs_all.append(obj)
+            if force or not os.path.exists(obj) or os.path.getmtime(obj) < max(os.path.getmtime(src), hdr):
+                todo.append((u + variant[0], src, obj, variant[1]))
 
     def compile_one(item):
-        u, src, obj = item
-        cmd = [nvcc, *ARCH, *FLAGS, *(["-DLNB_TRACE"] if trace else []), "-c", src, "-o", obj]
+        u, src, obj, extra = item
+        cmd = [nvcc, *ARCH, *FLAGS, *extra, *(["-DLNB_TRACE"] if trace else []), "-c", src, "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -67,7 +72,7 @@ def build(force=False, verbose=False, trace=False):
                     sys.stderr.write(f"--- nvcc {u} ---\n{r.stdout}{r.stderr}\n")
                 if r.returncode != 0:
                     raise RuntimeError(f"nvcc failed on csrc/{u}.cu")
-    objs = [os.path.join(OBJ_DIR, u + ".o") for u in units]
+    objs = objs_all
     if todo or not os.path.exists(LIB) or any(os.path.getmtime(o) > os.path.getmtime(LIB) for o in objs):
         r = subprocess.run([nvcc, "-shared", *ARCH, "-o", LIB, *objs], capture_output=True, text=True)
         if r.returncode != 0:

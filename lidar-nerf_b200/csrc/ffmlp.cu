@@ -211,6 +211,20 @@ int launch_fwd(const void *inputs, const void *weights, uint32_t B, const Shape 
 
 using namespace lnb;
 
+// bf16 build of this unit (-DLNB_BF16, see mlp_tiles.cuh): every entry point gets the suffix `_bf16`
+#ifdef LNB_BF16
+#define lnb_ffmlp_forward_ex lnb_ffmlp_forward_ex_bf16
+#define lnb_ffmlp_forward lnb_ffmlp_forward_bf16
+#define lnb_ffmlp_inference lnb_ffmlp_inference_bf16
+#define lnb_ffmlp_backward_workspace_bytes lnb_ffmlp_backward_workspace_bytes_bf16
+#define lnb_ffmlp_backward_accumulate_rows lnb_ffmlp_backward_accumulate_rows_bf16
+#define lnb_ffmlp_backward_accumulate lnb_ffmlp_backward_accumulate_bf16
+#define lnb_ffmlp_backward lnb_ffmlp_backward_bf16
+#define lnb_allocate_splitk lnb_allocate_splitk_bf16
+#define lnb_free_splitk lnb_free_splitk_bf16
+#define lnb_debug_bwd_trace_generic lnb_debug_bwd_trace_generic_bf16
+#endif
+
 extern "C" {
 
 int lnb_ffmlp_forward(const void *inputs, const void *weights, uint32_t B, uint32_t input_dim,

@@ -111,15 +111,15 @@ k_ray_dir_terms(const float *__restrict__ rays_d, const __half *__restrict__ w_h
                     const float arg = scalbnf(d[a], (int)f);
                     v = __sinf(arg + (r >= 3 ? 1.f : 0.f) * half_pi);
                 }
-                const __half hv = __float2half_rn(v);
-                ray_enc[(size_t)n * in_pad + j] = hv;
-                e[sub][j] = __half2float(hv);
+                const unsigned short hv = mlp_from_float(v);
+                reinterpret_cast<unsigned short *>(ray_enc)[(size_t)n * in_pad + j] = hv;
+                e[sub][j] = mlp_to_float(hv);
             }
         __syncthreads();
         if (live) {
             const __half *wr = w + h * pitch;
             float acc = 0.f;
-            for (uint32_t j = 0; j < nfreq; ++j) acc = fmaf(__half2float(wr[j]), e[sub][j], acc);
+            for (uint32_t j = 0; j < nfreq; ++j) acc = fmaf(mlp_to_float(wr[j]), e[sub][j], acc);
             ray_bias[(size_t)n * kHid + h] = acc;
         }
     }
@@ -313,19 +313,19 @@ k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const _
                 uint32_t v[16];
                 tmem_ld16(d_out + lane_sel, v);
                 tmem_ld_wait();
-                __half hv[16];
+                __align__(16) unsigned short hv[16];
 #pragma unroll
-                for (uint32_t k = 0; k < 16; ++k) hv[k] = __float2half_rn(__uint_as_float(v[k]));
+                for (uint32_t k = 0; k < 16; ++k) hv[k] = mlp_from_float(__uint_as_float(v[k]));
                 const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
                 uint4 *dst = reinterpret_cast<uint4 *>(sig_out + r * kOut);
                 dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                 dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-                sigma[r] = __expf(__half2float(hv[0])) * density_scale;    // activation.py:6-20 (forward)
+                sigma[r] = __expf(mlp_to_float(hv[0])) * density_scale;    // activation.py:6-20 (forward)
                 // head operand: zeros over the K range, geo_feat = sig_out[1..15] at columns geo_off .. geo_off+14
                 for (uint32_t c = 0; c < 2 * ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
 #pragma unroll
                 for (uint32_t k = 1; k < 16; ++k)
-                    sts16(tile_elem_addr(s_h, row, fs.geo_off + k - 1), __half_as_ushort(hv[k]));
+                    sts16(tile_elem_addr(s_h, row, fs.geo_off + k - 1), hv[k]);
             }
             fence_proxy_async();
             fence_before_sync();
@@ -357,8 +357,8 @@ k_field_fwd(const __half *__restrict__ X, const __half *__restrict__ Ws, const _
                 uint32_t v[16];
                 tmem_ld16(d_out + lane_sel, v);
                 tmem_ld_wait();
-                const float a = __half2float(__float2half_rn(__uint_as_float(v[0])));
-                const float b = __half2float(__float2half_rn(__uint_as_float(v[1])));
+                const float a = mlp_to_float(mlp_from_float(__uint_as_float(v[0])));
+                const float b = mlp_to_float(mlp_from_float(__uint_as_float(v[1])));
                 reinterpret_cast<float2 *>(rgb)[r] = make_float2(1.f / (1.f + __expf(-a)), 1.f / (1.f + __expf(-b)));
             }
             fence_before_sync();   // orders this tile's TMEM reads before the next tile's MMAs (released by `ready`)
@@ -409,6 +409,16 @@ int sm_count_field() {
 }  // namespace lnb
 
 using namespace lnb;
+
+// bf16 build of this unit (-DLNB_BF16, see mlp_tiles.cuh): every entry point gets the suffix `_bf16`
+#ifdef LNB_BF16
+#define lnb_field_supported lnb_field_supported_bf16
+#define lnb_field_ray_terms lnb_field_ray_terms_bf16
+#define lnb_field_forward lnb_field_forward_bf16
+#define lnb_field_head_backward_rows lnb_field_head_backward_rows_bf16
+#define lnb_field_head_backward lnb_field_head_backward_bf16
+#define lnb_debug_bwd_trace_head lnb_debug_bwd_trace_head_bf16
+#endif
 
 extern "C" {
 

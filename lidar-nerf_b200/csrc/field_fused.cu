@@ -303,7 +303,8 @@ k_field_fused_fwd(const FusedArgs a) {
                     r1 = __float2half_rn(__half2float(r1) + w * __high2float(hv));
                 }
             }
-            return (uint32_t)__half_as_ushort(r0) | ((uint32_t)__half_as_ushort(r1) << 16);
+            // the table and its interpolation are fp16 (reference semantics); the MLP operand is this unit's element type
+            return (uint32_t)mlp_from_float(__half2float(r0)) | ((uint32_t)mlp_from_float(__half2float(r1)) << 16);
         };
 
         stage_coords(0);
@@ -435,26 +436,26 @@ k_field_fused_fwd(const FusedArgs a) {
                         uint32_t v[16];
                         tmem_ld16(d_out, v);
                         tmem_ld_wait();
-                        __half hv[16];
+                        __align__(16) unsigned short hv[16];
 #pragma unroll
-                        for (uint32_t j = 0; j < 16; ++j) hv[j] = __float2half_rn(__uint_as_float(v[j]));
+                        for (uint32_t j = 0; j < 16; ++j) hv[j] = mlp_from_float(__uint_as_float(v[j]));
                         const uint32_t *pw = reinterpret_cast<const uint32_t *>(hv);
                         uint4 *dst = reinterpret_cast<uint4 *>(a.sig_out + r * kOut);
                         dst[0] = make_uint4(pw[0], pw[1], pw[2], pw[3]);
                         dst[1] = make_uint4(pw[4], pw[5], pw[6], pw[7]);
-                        a.sigma[r] = __expf(__half2float(hv[0])) * a.density_scale;    // activation.py:6-20 (forward)
+                        a.sigma[r] = __expf(mlp_to_float(hv[0])) * a.density_scale;    // activation.py:6-20 (forward)
                         __syncwarp();                        // copy-out of the last hidden layer is done with these rows
                         for (uint32_t c = 0; c < 2 * fs.ks_geo; ++c) sts128(tile_chunk_addr(s_h, row, c), make_uint4(0, 0, 0, 0));
 #pragma unroll
-                        for (uint32_t j = 1; j < 16; ++j) sts16h(elem_addr(s_h, row, fs.geo_off + j - 1), __half_as_ushort(hv[j]));
+                        for (uint32_t j = 1; j < 16; ++j) sts16h(elem_addr(s_h, row, fs.geo_off + j - 1), hv[j]);
                         publish(ready);
                     } else {
                         // head output -> (ray-drop, intensity) = sigmoid(fp16(h[0:2]))   (network.py:230)
                         uint32_t v[16];
                         tmem_ld16(d_out, v);
                         tmem_ld_wait();
-                        const float x0 = __half2float(__float2half_rn(__uint_as_float(v[0])));
-                        const float x1 = __half2float(__float2half_rn(__uint_as_float(v[1])));
+                        const float x0 = mlp_to_float(mlp_from_float(__uint_as_float(v[0])));
+                        const float x1 = mlp_to_float(mlp_from_float(__uint_as_float(v[1])));
                         reinterpret_cast<float2 *>(a.rgb)[r] = make_float2(1.f / (1.f + __expf(-x0)), 1.f / (1.f + __expf(-x1)));
                         fence_before_sync();                 // this tile's TMEM reads are ordered before the next tile's MMAs
                         if (k0 + t + kSlots < n_my) arrive_warp(ready);                // the slot's next tile may start
@@ -567,6 +568,13 @@ int sm_count_fused() {
 }  // namespace lnb
 
 using namespace lnb;
+
+// bf16 build of this unit (-DLNB_BF16, see mlp_tiles.cuh): every entry point gets the suffix `_bf16`
+#ifdef LNB_BF16
+#define lnb_field_fused_weight_bytes lnb_field_fused_weight_bytes_bf16
+#define lnb_field_pack_weights lnb_field_pack_weights_bf16
+#define lnb_field_fused_forward lnb_field_fused_forward_bf16
+#endif
 
 extern "C" {
 

@@ -427,7 +427,7 @@ k_mlp_bwd(const BwdArgs a) {
                     uint32_t v[32];
                     tmem_ld32(d_mine, v);
                     tmem_ld_wait();
-                    const float h0 = __half2float(__ushort_as_half((unsigned short)(hr.so_lo.x & 0xffffu)));
+                    const float h0 = mlp_to_float((unsigned short)(hr.so_lo.x & 0xffffu));
                     const float g0 = hr.gs * a.density_scale * __expf(fminf(fmaxf(h0, -15.f), 15.f));   // activation.py:14-17
                     float o[16];
                     o[0] = g0;
@@ -456,10 +456,11 @@ k_mlp_bwd(const BwdArgs a) {
                             const uint32_t col = half * 32 + c * 8;
                             if (col < cols) {
                                 uint4 pk;
-                                pk.x = pack_half2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
-                                pk.y = pack_half2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
-                                pk.z = pack_half2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
-                                pk.w = pack_half2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
+                                // (the input gradient is ALWAYS fp16: the hash-grid scatter reads it)
+                                pk.x = pack_f16x2(__uint_as_float(v[c * 8 + 0]), __uint_as_float(v[c * 8 + 1]));
+                                pk.y = pack_f16x2(__uint_as_float(v[c * 8 + 2]), __uint_as_float(v[c * 8 + 3]));
+                                pk.z = pack_f16x2(__uint_as_float(v[c * 8 + 4]), __uint_as_float(v[c * 8 + 5]));
+                                pk.w = pack_f16x2(__uint_as_float(v[c * 8 + 6]), __uint_as_float(v[c * 8 + 7]));
                                 *reinterpret_cast<uint4 *>(a.dX + r * sh.in_dim + t * 64 + col) = pk;
                             }
                         }

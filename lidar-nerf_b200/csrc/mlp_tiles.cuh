@@ -1,6 +1,8 @@
 // Tile movers, UMMA issue helpers and warpgroup utilities shared by the fused-MLP kernels (ffmlp.cu, field.cu).
 // Everything here is file-local to the including translation unit (anonymous namespace).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "tcgen05.cuh"
 
@@ -60,7 +62,31 @@ __device__ __forceinline__ void store_tile_rows(uint32_t tile, __half *__restric
     }
 }
 
+// ---- the MLP element type of this translation unit -------------------------------------------------------------
+// Weights, activations and activation gradients are 16-bit: fp16 by default, bf16 when the unit is compiled with
+// -DLNB_BF16 (build.py compiles field.cu / field_fused.cu / ffmlp.cu a second time that way and the entry points get the
+// suffix `_bf16`: BASELINE config 5, "bf16 MLP on tensor cores").  Pointers stay `__half *` = "16-bit element"; only the
+// conversions below and the tcgen05 operand format (tcgen05.cuh) know the difference.  fp32 accumulation either way.
+#ifdef LNB_BF16
+#define LNB_SYM(name) name##_bf16
 __device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float mlp_to_float(unsigned short bits) { return __uint_as_float((uint32_t)bits << 16); }
+__device__ __forceinline__ unsigned short mlp_from_float(float v) { return __bfloat16_as_ushort(__float2bfloat16_rn(v)); }
+#else
+#define LNB_SYM(name) name
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t *>(&h);
+}
+__device__ __forceinline__ float mlp_to_float(unsigned short bits) { return __half2float(__ushort_as_half(bits)); }
+__device__ __forceinline__ unsigned short mlp_from_float(float v) { return __half_as_ushort(__float2half_rn(v)); }
+#endif
+__device__ __forceinline__ float mlp_to_float(__half v) { return mlp_to_float(__half_as_ushort(v)); }
+// always fp16 (gradients handed to the hash-grid scatter, which reads fp16)
+__device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
     __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<uint32_t *>(&h);
 }

@@ -118,11 +118,18 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo
            ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
 }
 
-// Instruction descriptor for kind::f16 with fp16 A/B and fp32 accumulation:
-//   [4,6) D format (1 = f32)   [7,10) A format (0 = f16)   [10,13) B format (0 = f16)
+// Instruction descriptor for kind::f16 with 16-bit A/B and fp32 accumulation:
+//   [4,6) D format (1 = f32)   [7,10) A format (0 = f16, 1 = bf16)   [10,13) B format (0 = f16, 1 = bf16)
 //   [15] A major (0 = K, 1 = MN)   [16] B major   [17,23) N >> 3   [24,29) M >> 4
+// The operand format is the translation unit's MLP element type (mlp_tiles.cuh: fp16, or bf16 with -DLNB_BF16).
+#ifdef LNB_BF16
+constexpr uint32_t kOperandFormat = 1u;
+#else
+constexpr uint32_t kOperandFormat = 0u;
+#endif
 __host__ __device__ constexpr uint32_t instr_desc_f16(uint32_t M, uint32_t N, uint32_t a_mn, uint32_t b_mn) {
-    return (1u << 4) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) | ((M >> 4) << 24);
+    return (1u << 4) | (kOperandFormat << 7) | (kOperandFormat << 10) | (a_mn << 15) | (b_mn << 16) | ((N >> 3) << 17) |
+           ((M >> 4) << 24);
 }
 
 // D[tmem] (+)= A[smem] * B[smem]; issued by ONE thread.

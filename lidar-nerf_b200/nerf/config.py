@@ -24,6 +24,10 @@ class FieldConfig:
     desired_resolution: int = 32768
     log2_hashmap_size: int = 19
     # MLPs (ffmlp 64x2 each; network.py:45-99 shapes)
+    mlp_dtype: str = "fp16"              # "fp16" | "bf16": element type of the MLP weights / activations / activation
+                                         # gradients on the tensor cores (fp32 accumulation either way; the hash table and
+                                         # its gradient path stay fp16 / fp32).  bf16 = BASELINE config 5; needs the
+                                         # persistent forward kernel (fused_gather)
     hidden_dim: int = 64
     sigma_layers: int = 2                # FFMLP num_layers
     head_layers: int = 2

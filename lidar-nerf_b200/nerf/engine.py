@@ -45,6 +45,7 @@ class LidarFieldEngine:
         gradient vector (the caller hands a gradient buffer to `set_grad_buffer` before the backward kernels run)."""
         self.cfg = cfg
         self.external_params = bool(external_params)
+        self._sfx = "_bf16" if cfg.mlp_dtype == "bf16" else ""
         self.dev = torch.device(device)
         self.N = int(n_rays)
         c = cfg
@@ -119,6 +120,19 @@ class LidarFieldEngine:
         self.table_h = self.Ph[:n_table].view(self.n_rows, c.level_dim)
         self.w_sigma_h = self.Ph[n_table:n_table + n_sigma]
         self.w_head_h = self.Ph[n_table + n_sigma:n]
+        # bf16 MLPs (cfg.mlp_dtype): the kernels' `_bf16` builds read the weights from a separate bf16 copy of the MLP part
+        # of the parameters (36 KB), refreshed inside the step from the fp32 master (one rank) or the fp16 shadow (data
+        # parallel / external parameters); the table part of the shadow stays fp16
+        self.bf16 = c.mlp_dtype == "bf16"
+        if c.mlp_dtype not in ("fp16", "bf16"):
+            raise ValueError(f"mlp_dtype={c.mlp_dtype!r}: choose fp16 or bf16")
+        self.mlp_torch_dtype = torch.bfloat16 if self.bf16 else torch.float16
+        self._sfx = "_bf16" if self.bf16 else ""
+        if self.bf16:
+            self.w_mlp_bf16 = torch.zeros(n_sigma + n_head, dtype=torch.bfloat16, device=dev)
+            self.w_sigma_h = self.w_mlp_bf16[:n_sigma]
+            self.w_head_h = self.w_mlp_bf16[n_sigma:]
+            self._refresh_bf16_weights()
         if self.G is not None:
             self.set_grad_buffer(self.G)
         self.step_count = 0
@@ -155,18 +169,22 @@ class LidarFieldEngine:
         self.dt_max = np.float32(two_sqrt3) * np.float32(1 << (c.cascade - 1)) / np.float32(c.grid_size)
 
         # fused field kernels: per-ray direction terms instead of a per-sample [M, 96] head input
-        self.fused = bool(c.fused_field) and lib.lnb_field_supported(
+        self.fused = bool(c.fused_field) and self._fn("lnb_field_supported")(
             u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
             u32(c.hidden_dim)) == 0
         if c.dir_encoding == "sh" and not self.fused:
             raise RuntimeError("dir_encoding='sh' is implemented by the fused field kernels only (fused_field=True, "
                                "SH degree 4, 64-wide 2-layer MLPs)")
         # gather + MLPs as one persistent kernel: the MLP weights travel as a pre-laid-out shared-memory image (TMA)
-        wbytes = int(lib.lnb_field_fused_weight_bytes(u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim),
+        self._fn("lnb_field_fused_weight_bytes").restype = C.c_size_t
+        wbytes = int(self._fn("lnb_field_fused_weight_bytes")(u32(self.enc_dim), u32(c.sigma_layers), u32(c.head_in_dim),
                                                       u32(c.head_layers), u32(c.dir_code), u32(c.hidden_dim)))
         self.fused_gather = bool(c.fused_gather) and self.fused and wbytes > 0 and c.level_dim == 2
+        if self.bf16 and not self.fused_gather:
+            raise RuntimeError("mlp_dtype='bf16' needs the persistent forward kernel (fused_field and fused_gather, "
+                               "level_dim 2): the stand-alone grid encoder writes fp16 features")
         self.wimage = torch.zeros(max(wbytes, 16), dtype=torch.uint8, device=dev) if self.fused_gather else None
-        self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=torch.float16, device=dev)
+        self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=self.mlp_torch_dtype, device=dev)
         self.ray_bias = torch.zeros(N, c.hidden_dim, **f)
 
         # cross-step pipelining (graph mode, one rank): the captured step BEGINS with the Adam update of the previous
@@ -184,6 +202,15 @@ class LidarFieldEngine:
         self._alloc_samples(sample_budget or N * 64)
 
     # ------------------------------------------------------------------------------------------------------
+    def _fn(self, name):
+        """C-ABI entry point of the MLP kernels for this engine's element type (`name` or `name_bf16`)."""
+        return getattr(lib, name + self._sfx)
+
+    def _refresh_bf16_weights(self):
+        a, n = self.n_table, self.n_params
+        src = self.P[a:n] if (self.P is not None and self.ex.world == 1) else self.Ph[a:n]
+        self.w_mlp_bf16.copy_(src)
+
     def set_grad_buffer(self, G):
         """Flat fp32 gradient vector [hash table | density MLP | LiDAR head] the backward kernels accumulate into."""
         a, b, n = self.n_table, self.n_table + self.n_sigma, self.n_params
@@ -195,7 +222,7 @@ class LidarFieldEngine:
     def load_params(self, embeddings, w_sigma, w_head):
         """fp32 (or fp16) parameters owned by the caller -> the fp16 shadow the kernels read (three cast-copies)."""
         self.table_h.copy_(embeddings.detach().reshape(self.n_rows, self.cfg.level_dim))
-        self.w_sigma_h.copy_(w_sigma.detach().reshape(-1))
+        self.w_sigma_h.copy_(w_sigma.detach().reshape(-1))          # (fp16 shadow slice, or the bf16 copy in bf16 mode)
         self.w_head_h.copy_(w_head.detach().reshape(-1))
 
     # ------------------------------------------------------------------------------------------------------
@@ -207,7 +234,7 @@ class LidarFieldEngine:
         self._graph = None
         dev, c = self.dev, self.cfg
         f = dict(dtype=torch.float32, device=dev)
-        h = dict(dtype=torch.float16, device=dev)
+        h = dict(dtype=self.mlp_torch_dtype, device=dev)          # MLP-typed rows (fp16, or bf16 with mlp_dtype="bf16")
         self.xyzs = torch.zeros(M, 3, **f)
         self.dirs = torch.zeros(M, 3, **f) if not self.fused else None
         self.ray_ids = torch.zeros(M, dtype=torch.int32, device=dev)
@@ -227,7 +254,7 @@ class LidarFieldEngine:
         self.g_sigma = torch.zeros(M, **f)
         self.g_rgb = torch.zeros(M, 2, **f)
         self.g_sig_out = torch.empty(M, 16, **h)
-        self.g_enc = torch.empty(M, self.enc_dim, **h)
+        self.g_enc = torch.empty(M, self.enc_dim, dtype=torch.float16, device=dev)   # always fp16: read by the scatter
 
     @staticmethod
     def _s():
@@ -274,11 +301,13 @@ class LidarFieldEngine:
             # per-ray direction terms depend only on rays_d and the head weights: a side branch next to the gather
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
-                _ck(lib.lnb_field_ray_terms(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.dir_code),
+                if self.bf16:
+                    self._refresh_bf16_weights()           # 18 k weights: fp32 master / fp16 shadow -> bf16 operand copy
+                _ck(self._fn("lnb_field_ray_terms")(p(self.rays_d), p(self.w_head_h), u32(N), u32(c.dir_code),
                                             u32(c.head_in_dim), p(self.ray_enc), p(self.ray_bias), self._s()),
                     "ray_terms")
                 if self.fused_gather:
-                    _ck(lib.lnb_field_pack_weights(p(self.w_sigma_h), p(self.w_head_h), u32(self.enc_dim),
+                    _ck(self._fn("lnb_field_pack_weights")(p(self.w_sigma_h), p(self.w_head_h), u32(self.enc_dim),
                                                    u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
                                                    u32(c.dir_code), u32(c.hidden_dim), p(self.wimage), self._s()),
                         "pack_weights")
@@ -292,7 +321,7 @@ class LidarFieldEngine:
         nl = vp(self.counter.data_ptr() + 8)          # counter[2]: live rows, counted by the compositing kernel
         if self.fused_gather:
             main.wait_stream(self._side)               # join: ray terms + weight image ready
-            _ck(lib.lnb_field_fused_forward(p(self.xyzs), p(self.table_h), p(self.offsets), u32(c.num_levels),
+            _ck(self._fn("lnb_field_fused_forward")(p(self.xyzs), p(self.table_h), p(self.offsets), u32(c.num_levels),
                                             u32(c.level_dim), f32(self.S), u32(c.base_resolution), f32(c.bound),
                                             p(self.wimage), p(self.ray_ids), p(self.ray_bias), u32(M),
                                             u32(c.sigma_layers), u32(c.head_in_dim), u32(c.head_layers),
@@ -306,7 +335,7 @@ class LidarFieldEngine:
             "grid_fwd")
         if self.fused:
             main.wait_stream(self._side)               # join: ray terms ready
-            _ck(lib.lnb_field_forward(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
+            _ck(self._fn("lnb_field_forward")(p(self.enc), p(self.w_sigma_h), p(self.w_head_h), p(self.ray_ids),
                                       p(self.ray_bias), u32(M), u32(self.enc_dim), u32(c.sigma_layers),
                                       u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code), u32(c.hidden_dim),
                                       f32(c.density_scale), p(self.fb_sigma), p(self.sig_out), p(self.sigma),
@@ -401,12 +430,12 @@ class LidarFieldEngine:
             # backward on the live rows only: g_sig_out / g_enc are in compact order, everything saved by the forward
             # pass is read through live_idx
             li = p(self.live_idx)
-            _ck(lib.lnb_field_head_backward_rows(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
+            _ck(self._fn("lnb_field_head_backward_rows")(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                                  p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
                                                  u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
                                                  u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
                                                  p(self.g_head_w), li, nl, s), "field_head_backward_rows")
-            _ck(lib.lnb_ffmlp_backward_accumulate_rows(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h),
+            _ck(self._fn("lnb_ffmlp_backward_accumulate_rows")(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h),
                                                        p(self.fb_sigma), u32(M), u32(self.enc_dim), u32(16),
                                                        u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), i32(1),
                                                        p(self.g_enc), p(self.g_sigma_w), li, nl, s),
@@ -419,7 +448,7 @@ class LidarFieldEngine:
                                                   f32(c.bound), i32(1), li, nl, s), "grid_bwd_rows")
             return
         if self.fused:
-            _ck(lib.lnb_field_head_backward(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
+            _ck(self._fn("lnb_field_head_backward")(p(self.g_rgb), p(self.rgb), p(self.g_sigma), p(self.sig_out),
                                             p(self.ray_ids), p(self.ray_enc), p(self.w_head_h), p(self.fb_head),
                                             u32(M), u32(c.head_in_dim), u32(c.head_layers), u32(c.dir_code),
                                             u32(c.hidden_dim), f32(c.density_scale), p(self.g_sig_out),
@@ -434,7 +463,7 @@ class LidarFieldEngine:
             _ck(lib.lnb_field_sigma_out_grad(p(self.g_sigma), p(self.sig_out), p(self.g_head_in), u32(M),
                                              u32(c.head_in_dim), u32(c.freq_degree), f32(c.density_scale),
                                              p(self.g_sig_out), na, s), "sigma_out_grad")
-        _ck(lib.lnb_ffmlp_backward_accumulate(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h), p(self.fb_sigma),
+        _ck(self._fn("lnb_ffmlp_backward_accumulate")(p(self.g_sig_out), p(self.enc), p(self.w_sigma_h), p(self.fb_sigma),
                                               u32(M), u32(self.enc_dim), u32(16), u32(c.hidden_dim),
                                               u32(c.sigma_layers), u32(0), u32(6), i32(1), p(self.g_enc),
                                               p(self.g_sigma_w), na, s), "ffmlp_bwd(sigma)")
@@ -769,8 +798,15 @@ class LidarFieldEngine:
                                            u32(c.level_dim), u32(c.num_levels), f32(self.S), u32(c.base_resolution),
                                            vp(0), u32(0), i32(0), u32(0), i32(1), i32(1), f32(c.bound), vp(0), s),
             "grid_fwd")
-        out = torch.empty(Bp, 16, dtype=torch.float16, device=self.dev)
-        ff.ffmlp_inference(enc, self.w_sigma_h, Bp, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6, None, out)
+        out = torch.empty(Bp, 16, dtype=self.mlp_torch_dtype, device=self.dev)
+        if self.bf16:
+            self._refresh_bf16_weights()
+            enc = enc.to(torch.bfloat16)
+            _ck(lib.lnb_ffmlp_inference_bf16(p(enc), p(self.w_sigma_h), u32(Bp), u32(self.enc_dim), u32(16),
+                                             u32(c.hidden_dim), u32(c.sigma_layers), u32(0), u32(6), vp(0), p(out), s),
+                "ffmlp_inference_bf16")
+        else:
+            ff.ffmlp_inference(enc, self.w_sigma_h, Bp, self.enc_dim, 16, c.hidden_dim, c.sigma_layers, 0, 6, None, out)
         return torch.exp(out[:B, 0].float()) * c.density_scale
 
     @torch.no_grad()

@@ -75,8 +75,12 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
     """Returns dict(loss, grad (flat fp32, unscaled), counts, ws, depth, image, n_samples)."""
     c = params.cfg
     N = rays_o.shape[0]
+    bf16 = getattr(c, "mlp_dtype", "fp16") == "bf16"
+    orc.set_mlp_dtype("bf16" if bf16 else "fp16")
     Ph = orc.to_half(params.P)
     table, w_sigma, w_head = params.split(Ph)
+    if bf16:      # the MLP weights are the bf16 rounding of the fp32 master (the table stays fp16)
+        _, w_sigma, w_head = params.split(orc.to_bf16(params.P))
     nears = np.full(N, c.min_near_lidar, np.float32)
     fars = nears * np.float32(c.far_factor)
     xyzs, dirs, deltas, rays, counter = orc.march_rays_train(rays_o, rays_d, c.bound, bitfield, c.cascade, c.grid_size,
@@ -88,6 +92,7 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
     x01 = ((xyzs + np.float32(c.bound)) * np.float32(1.0 / (2.0 * c.bound))).astype(np.float32)
     enc = orc.grid_encode_forward(x01, table, params.offsets, params.pls, c.base_resolution, 0, False, 0, True, False,
                                   level_scales)
+    enc = orc.mlp_round(enc)       # (fp16 interpolation result -> the MLP's operand type)
     sig_out, fb_s = orc.ffmlp_forward(enc, w_sigma, params.enc_dim, 16, c.hidden_dim, c.sigma_layers)
     sigma = np.exp(sig_out[:, 0]).astype(np.float32) * np.float32(c.density_scale)
     # direction encoding of the head: frequency (network.py:83) or spherical harmonics (network.py:64), cfg.dir_encoding
@@ -98,7 +103,7 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
     head_in = np.zeros((M, c.head_in_dim), np.float32)
     head_in[:, :fenc.shape[1]] = fenc
     head_in[:, fenc.shape[1]:fenc.shape[1] + 15] = sig_out[:, 1:16]
-    head_in = orc.to_half(head_in)
+    head_in = orc.mlp_round(head_in)
     head_out, fb_h = orc.ffmlp_forward(head_in, w_head, c.head_in_dim, 16, c.hidden_dim, c.head_layers)
     rgb = (1.0 / (1.0 + np.exp(-head_out[:, :2]))).astype(np.float32)
     ws, depth, image = orc.composite_rays_train_forward(sigma, rgb, deltas, rays, c.T_thresh)
@@ -121,12 +126,13 @@ def field_step(params: FieldParams, rays_o, rays_d, gt, noises, bitfield, M, lev
     g_sig_out[:, 0] = g_sigma * np.float32(c.density_scale) * np.exp(np.clip(sig_out[:, 0], -15, 15))
     g_sig_out[:, 1:16] = g_head_in[:, fenc.shape[1]:fenc.shape[1] + 15]
     g_enc, gw_sigma, _ = orc.ffmlp_backward(g_sig_out, enc, w_sigma, fb_s, params.enc_dim, 16, c.hidden_dim,
-                                            c.sigma_layers, True)
+                                            c.sigma_layers, True, grad_inputs_fp16=True)
     g_table = orc.grid_encode_backward(orc.to_half(g_enc), x01, table.shape, params.offsets, params.pls, c.base_resolution,
                                        0, False, 0, False, None, level_scales)
     grad = np.concatenate([g_table.reshape(-1), gw_sigma, gw_head]).astype(np.float32)
     if apply_adam:
         params.step += 1
         orc.adam_step(params.P, grad, params.m, params.v, c.lr, c.beta1, c.beta2, c.eps, params.step, 1.0 / c.loss_scale)
+    orc.set_mlp_dtype("fp16")
     return dict(loss=loss, grad=grad, counts=rays[:, 2].copy(), ws=ws, depth=depth, image=image,
                 n_samples=int(counter[0]), sigma=sigma, rgb=rgb, enc=enc, sig_out=sig_out, head_out=head_out)

@@ -33,6 +33,23 @@
 
 static inline float clampf(float x, float lo, float hi) { return fminf(hi, fmaxf(lo, x)); }
 static inline float to_half_precision(float v) { return (float)(_Float16)v; }
+/* bf16 (round to nearest even on the upper 16 bits of the fp32 pattern), for the bf16 build of the MLP kernels */
+static inline float to_bf16_precision(float v) {
+    uint32_t u;
+    memcpy(&u, &v, 4);
+    if ((u & 0x7fffffffu) > 0x7f800000u) return v;               /* NaN */
+    u += 0x7fffu + ((u >> 16) & 1u);
+    u &= 0xffff0000u;
+    memcpy(&v, &u, 4);
+    return v;
+}
+/* element type of the fused MLPs: 0 = fp16 (default); bit 0 = bf16 activations / weights / activation gradients;
+ * bit 1 = the INPUT gradient (grad_inputs) is nevertheless rounded to fp16 (the density MLP hands it to the hash-grid
+ * scatter, which reads fp16).  Set by orc_set_mlp_mode; mirrors -DLNB_BF16 of lidar-nerf_b200/csrc/mlp_tiles.cuh. */
+static int g_mlp_mode = 0;
+ORC_API void orc_set_mlp_mode(int mode) { g_mlp_mode = mode; }
+static inline float mlp_round(float v) { return (g_mlp_mode & 1) ? to_bf16_precision(v) : to_half_precision(v); }
+static inline float mlp_round_dx(float v) { return ((g_mlp_mode & 1) && !(g_mlp_mode & 2)) ? to_bf16_precision(v) : to_half_precision(v); }
 
 ORC_API int orc_max_threads(void) {
 #ifdef _OPENMP
@@ -584,7 +601,7 @@ ORC_API void orc_ffmlp_forward(const float *inputs, const float *weights, uint32
         for (uint32_t j = 0; j < hidden; ++j) {
             float acc = 0;
             for (uint32_t i = 0; i < in_dim; ++i) acc += inputs[(size_t)b * in_dim + i] * w_in[(size_t)j * in_dim + i];
-            cur[j] = to_half_precision(fmaxf(acc, 0.f));
+            cur[j] = mlp_round(fmaxf(acc, 0.f));
         }
         if (forward_buffer) memcpy(forward_buffer + ((size_t)0 * B + b) * hidden, cur, sizeof(float) * hidden);
         for (uint32_t l = 0; l + 1 < num_layers; ++l) {
@@ -592,7 +609,7 @@ ORC_API void orc_ffmlp_forward(const float *inputs, const float *weights, uint32
             for (uint32_t j = 0; j < hidden; ++j) {
                 float acc = 0;
                 for (uint32_t i = 0; i < hidden; ++i) acc += cur[i] * w[(size_t)j * hidden + i];
-                nxt[j] = to_half_precision(fmaxf(acc, 0.f));
+                nxt[j] = mlp_round(fmaxf(acc, 0.f));
             }
             memcpy(cur, nxt, sizeof(float) * hidden);
             if (forward_buffer) memcpy(forward_buffer + ((size_t)(l + 1) * B + b) * hidden, cur, sizeof(float) * hidden);
@@ -600,7 +617,7 @@ ORC_API void orc_ffmlp_forward(const float *inputs, const float *weights, uint32
         for (uint32_t o = 0; o < out_dim; ++o) {
             float acc = 0;
             for (uint32_t i = 0; i < hidden; ++i) acc += cur[i] * w_out[(size_t)o * hidden + i];
-            outputs[(size_t)b * out_dim + o] = to_half_precision(acc);
+            outputs[(size_t)b * out_dim + o] = mlp_round(acc);
         }
     }
 }
@@ -623,7 +640,7 @@ ORC_API void orc_ffmlp_backward(const float *grad, const float *inputs, const fl
         for (uint32_t j = 0; j < hidden; ++j) {
             float acc = 0;
             for (uint32_t o = 0; o < out_dim; ++o) acc += g[o] * w_out[(size_t)o * hidden + j];
-            d_cur[j] = to_half_precision(h_last[j] > 0 ? acc : 0.f);
+            d_cur[j] = mlp_round(h_last[j] > 0 ? acc : 0.f);
         }
         if (backward_buffer) memcpy(backward_buffer + ((size_t)0 * B + b) * hidden, d_cur, sizeof(float) * hidden);
         for (int l = (int)num_layers - 2; l >= 0; --l) {   /* W_hid[l]: h_l -> h_{l+1} */
@@ -635,7 +652,7 @@ ORC_API void orc_ffmlp_backward(const float *grad, const float *inputs, const fl
             for (uint32_t j = 0; j < hidden; ++j) {
                 float acc = 0;
                 for (uint32_t o = 0; o < hidden; ++o) acc += d_cur[o] * w[(size_t)o * hidden + j];
-                d_nxt[j] = to_half_precision(h_prev[j] > 0 ? acc : 0.f);
+                d_nxt[j] = mlp_round(h_prev[j] > 0 ? acc : 0.f);
             }
             memcpy(d_cur, d_nxt, sizeof(float) * hidden);
             if (backward_buffer)
@@ -648,7 +665,7 @@ ORC_API void orc_ffmlp_backward(const float *grad, const float *inputs, const fl
             for (uint32_t i = 0; i < in_dim; ++i) {
                 float acc = 0;
                 for (uint32_t o = 0; o < hidden; ++o) acc += d_cur[o] * w_in[(size_t)o * in_dim + i];
-                grad_inputs[(size_t)b * in_dim + i] = to_half_precision(acc);
+                grad_inputs[(size_t)b * in_dim + i] = mlp_round_dx(acc);
             }
     }
 }

@@ -245,9 +245,31 @@ def to_half(a):
     return np.asarray(a, dtype=np.float32).astype(np.float16).astype(np.float32)
 
 
+def to_bf16(a):
+    """Round to bfloat16 (nearest even), returned as float32."""
+    u = np.ascontiguousarray(a, dtype=np.float32).view(np.uint32).astype(np.uint64)
+    u = (u + 0x7FFF + ((u >> 16) & 1)) & 0xFFFF0000
+    return u.astype(np.uint32).view(np.float32)
+
+
+_MLP_BF16 = False
+
+
+def set_mlp_dtype(name):
+    """Element type of the fused MLPs in ffmlp_forward / ffmlp_backward: "fp16" (default) or "bf16" (the -DLNB_BF16
+    build of the kernels)."""
+    global _MLP_BF16
+    _MLP_BF16 = name == "bf16"
+    lib().orc_set_mlp_mode(C.c_int(1 if _MLP_BF16 else 0))
+
+
+def mlp_round(a):
+    return to_bf16(a) if _MLP_BF16 else to_half(a)
+
+
 def ffmlp_forward(inputs, weights, input_dim, output_dim, hidden_dim, num_layers):
     """inputs [B,in], weights flat; both are rounded to fp16 first.  -> outputs [B,out], forward_buffer."""
-    x, w = to_half(inputs), to_half(weights).reshape(-1)
+    x, w = mlp_round(inputs), mlp_round(weights).reshape(-1)
     B = x.shape[0]
     fb = np.empty((num_layers, B, hidden_dim), np.float32)
     out = np.empty((B, output_dim), np.float32)
@@ -257,8 +279,11 @@ def ffmlp_forward(inputs, weights, input_dim, output_dim, hidden_dim, num_layers
 
 
 def ffmlp_backward(grad, inputs, weights, forward_buffer, input_dim, output_dim, hidden_dim, num_layers,
-                   calc_grad_inputs=True):
-    g, x, w = to_half(grad), to_half(inputs), to_half(weights).reshape(-1)
+                   calc_grad_inputs=True, grad_inputs_fp16=False):
+    """grad_inputs_fp16: in bf16 mode, round the input gradient to fp16 nevertheless (density MLP -> hash-grid scatter)."""
+    g, x, w = mlp_round(grad), mlp_round(inputs), mlp_round(weights).reshape(-1)
+    if _MLP_BF16:
+        lib().orc_set_mlp_mode(C.c_int(3 if grad_inputs_fp16 else 1))
     B = x.shape[0]
     bb = np.zeros((num_layers, B, hidden_dim), np.float32)
     gi = np.zeros((B, input_dim), np.float32) if calc_grad_inputs else None

@@ -146,6 +146,24 @@ def test_fused_step_with_patch_gradient_loss_matches_cpu_restatement():
     assert gpu["loss"] > base * 1.02, (gpu["loss"], base)
 
 
+@pytest.mark.parametrize("over", [dict(), dict(bound=4.0, max_steps=128, min_near_lidar=0.05)])
+def test_bf16_mlp_step_matches_cpu_restatement(over):
+    """BASELINE config 5: the MLPs in bf16 on the tensor cores (the `_bf16` builds of the kernels: tcgen05 kind::f16 with
+    bf16 operand formats, fp32 accumulation; the table stays fp16), also on the large-bound scene (bound 4 -> 3 cascades,
+    128 march steps).  Whole step - per-ray counts, outputs, loss, every gradient - against the CPU restatement run with
+    the same roundings (oracle.set_mlp_dtype("bf16"))."""
+    from oracle import check_engine
+    cfg = check_engine.small_config(mlp_dtype="bf16", **over)
+    eng, gpu, cpu = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg, seed=4)
+    assert eng.bf16 and eng.fused_gather and eng.fb_sigma.dtype == torch.bfloat16 and eng.cfg.cascade == (3 if over else 1)
+    assert gpu["n_samples"] > 1000
+    check_engine.compare(gpu, cpu, eng.n_table)
+    # and it is a different computation from the fp16 build: same inputs, visibly different rounding of the outputs
+    cfg16 = check_engine.small_config(**over)
+    _, gpu16, _ = check_engine.run_pair(n_rays=256, device=DEV, cfg=cfg16, seed=4)
+    assert np.abs(gpu16["image"] - gpu["image"]).max() > 1e-5
+
+
 def test_fused_composite_step_equals_the_three_kernel_chain():
     """lnb_lidar_composite_step = composite forward + lidar_loss + composite backward (+ the zero fill it removes)."""
     from oracle import check_engine

@@ -264,3 +264,46 @@ def test_trainer_train_step_equals_fused_engine_step(tmp_path):
         assert rel(g_head, ge[b:eng.n_params]) < 1e-2, rel(g_head, ge[b:eng.n_params])
     finally:
         _cleanup_modules()
+
+
+@pytest.mark.gpu
+def test_reference_network_class_equals_this_librarys_on_shared_weights():
+    """a15: the reference's OWN `lidarnerf/nerf/network.py:NeRFNetwork` (nn.Linear stacks; its encoders resolve to this
+    library through compat.install) and this library's `NeRFNetwork(use_ffmlp=False)` are the same function: identical
+    state_dict keys, and on shared weights identical `density()` / `color()` outputs and identical dense `render()`."""
+    root, kind = _ref_or_skip()
+    from lidar_nerf_b200 import compat
+    from lidar_nerf_b200.nerf.network import NeRFNetwork as Ours
+    try:
+        compat.install(networks=False)                  # keep the reference's network class, swap only the extensions
+        import importlib
+        ref_mod = importlib.import_module("lidarnerf.nerf.network")
+        assert ref_mod.NeRFNetwork is not Ours
+        kw = dict(encoding="hashgrid", desired_resolution=2048, log2_hashmap_size=15, num_layers=2, hidden_dim=64,
+                  geo_feat_dim=15, bound=1, density_scale=1, min_near=0.05, density_thresh=10, bg_radius=-1)
+        torch.manual_seed(0)
+        ref = ref_mod.NeRFNetwork(**kw).cuda().eval()
+        ours = Ours(use_ffmlp=False, **kw).cuda().eval()
+        assert sorted(ref.state_dict().keys()) == sorted(ours.state_dict().keys())
+        ours.load_state_dict(ref.state_dict())          # a reference checkpoint loads as is
+        ours.encoder.embeddings.data.uniform_(-0.5, 0.5)
+        ref.load_state_dict(ours.state_dict())
+        g = torch.Generator().manual_seed(1)
+        x = (torch.rand(4096, 3, generator=g) * 2 - 1).cuda()
+        d = torch.randn(4096, 3, generator=g)
+        d = (d / d.norm(dim=-1, keepdim=True)).cuda()
+        with torch.no_grad():
+            a, b = ref.density(x), ours.density(x)
+            assert torch.equal(a["sigma"], b["sigma"]) and torch.equal(a["geo_feat"], b["geo_feat"])
+            ca = ref.color(x, d, cal_lidar_color=True, geo_feat=a["geo_feat"])
+            cb = ours.color(x, d, cal_lidar_color=True, geo_feat=b["geo_feat"])
+            assert torch.equal(ca, cb)
+            o = torch.zeros(256, 3).cuda()
+            ra = ref.render(o[None], d[None, :256], cal_lidar_color=True, staged=False, perturb=False, num_steps=64,
+                            upsample_steps=16)
+            rb = ours.render(o[None], d[None, :256], cal_lidar_color=True, staged=False, perturb=False, num_steps=64,
+                             upsample_steps=16, cuda_ray="dense")
+        np.testing.assert_allclose(ra["depth_lidar"].cpu().numpy(), rb["depth_lidar"].cpu().numpy(), rtol=1e-4, atol=1e-6)
+        np.testing.assert_allclose(ra["image_lidar"].cpu().numpy(), rb["image_lidar"].cpu().numpy(), rtol=1e-4, atol=1e-6)
+    finally:
+        _cleanup_modules()
