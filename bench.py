@@ -389,7 +389,8 @@ def main():
     # ---- timed region: `--repeats` blocks of EXACTLY --steps steps each, the MEDIAN block is reported.  Preceded by
     # >= --spin-s seconds of untimed steps at load (a 20-step block lasts ~11 ms: without this the first block sees the
     # clock ramp from idle and whatever the freshly forked nvidia-smi sampler does to the driver).  `value` (inputs
-    # resident in HBM) and `e2e` (pinned host batch in, loss out, every step) are measured the same way, alternating.
+    # resident in HBM) and `e2e` (pinned host batch in, loss out, every step) are measured the same way: `--repeats`
+    # consecutive blocks each, both series started on a multiple of the grid-refresh interval (see align()).
     # A correct pair has value >= e2e (the e2e step does strictly more); the pair is re-measured up to twice if it does
     # not, and the run FAILS (exit 3) if it still does not.
     repeats = max(1, args.repeats)
@@ -407,15 +408,28 @@ def main():
     refresh_ms = r0.elapsed_time(r1)
     clocks.mark()
     attempts = []
+
+    def align():
+        """Untimed steps until the next step is number 1 (mod refresh interval): both arms then see the same placement of the
+        density-grid refreshes inside their blocks (a 20-step block holds one or two of the 0.67 ms refreshes depending on
+        where it starts; interleaving the two arms gave one of them all the two-refresh blocks)."""
+        k = max(cfg_interval, 1)
+        while eng.step_count % k != 0:
+            run(1, False)
+        torch.cuda.synchronize()
+
     for attempt in range(3):
+        align()
         launches0 = _lib.launch_count()
-        blocks, blocks_e2e = [], []
-        for r in range(repeats):
-            blocks.append(timed_block(False))
-            blocks_e2e.append(timed_block(True))
-        launches_region = _lib.launch_count() - launches0
+        blocks = [timed_block(False) for _ in range(repeats)]          # consecutive blocks of EXACTLY --steps steps
+        launches_mid = _lib.launch_count()
+        align()
+        blocks_e2e = [timed_block(True) for _ in range(repeats)]
+        launches_region = 2 * (launches_mid - launches0)      # (the value arm's share, counted for both arms alike below)
         ms, ms_e2e = median(blocks), median(blocks_e2e)
-        attempts.append({"value_blocks_ms": [round(x, 4) for x in blocks], "e2e_blocks_ms": [round(x, 4) for x in blocks_e2e]})
+        attempts.append({"value_blocks_ms": [round(x, 4) for x in blocks], "e2e_blocks_ms": [round(x, 4) for x in blocks_e2e],
+                         "value_mean_block_ms": round(sum(blocks) / len(blocks), 4),
+                         "e2e_mean_block_ms": round(sum(blocks_e2e) / len(blocks_e2e), 4)})
         if ms <= ms_e2e / 0.97:
             break
         spin(args.spin_s)
