@@ -193,6 +193,24 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
         : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// the same wait, tied to the registers of one tmem_ld16 by a data dependence: lets a SECOND load stay in flight across
+// the processing of the first without the compiler being free to move uses of `r` above the wait
+__device__ __forceinline__ void tmem_ld_wait16(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
+
+// compiler-only: uses of `r` stay below this point (placed after a tmem_ld_wait that covers several loads)
+__device__ __forceinline__ void tmem_ld_tie16(uint32_t (&r)[16]) {
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 
 // ---- the one operand layout ---------------------------------------------------------------------------
 // A tile is ROWS x 64 halves, row pitch 128 B, 16-byte chunk c of row r stored at chunk (c ^ (r & 7)).

@@ -1,4 +1,5 @@
 """GPU tests of the fused training engine and of the B2 (reference-shaped) Python wrappers."""
+import os
 import numpy as np
 import pytest
 import torch
@@ -39,31 +40,38 @@ def test_persistent_gather_field_kernel_is_bit_identical_to_the_two_kernel_forwa
     the TMA engine) == lnb_grid_encode_forward_ex -> lnb_field_forward, bit for bit, on everything the step keeps."""
     from oracle import check_engine
     out = {}
-    for fused_gather in (False, True):
-        for n_rays, over in ((256, {}), (1024, dict(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024))):
-            cfg = check_engine.small_config(fused_gather=fused_gather, perturb=False, **over)
-            if n_rays == 256:
-                eng, _, _ = check_engine.run_pair(n_rays=n_rays, device=DEV, cfg=cfg, seed=7)
-            else:
-                eng = _run_engine_only(cfg, n_rays)
-            assert eng.fused_gather == fused_gather
-            n = int(eng.counter[0])
-            assert n > 1000
-            # sample rows in ray order (the march hands out row offsets in arrival order, which differs between runs)
-            rays = eng.rays.cpu().numpy()
-            rays = rays[np.argsort(rays[:, 0])]
-            order = torch.from_numpy(np.concatenate([np.arange(o, o + k) for _, o, k in rays])).to(DEV)
-            assert len(order) == n
-            out[(fused_gather, n_rays)] = dict(enc=eng.enc[order], sigma=eng.sigma[order], rgb=eng.rgb[order],
-                                               sig_out=eng.sig_out[order], fb_s=eng.fb_sigma[:, order],
-                                               fb_h=eng.fb_head[:, order], G=eng.G.clone(), loss=float(eng.loss_acc))
+    # third leg: the persistent kernel with every level forced through its generic row indexing (`% hashmap_size`, FRND
+    # floor) instead of the dense / power-of-two-hash fast paths - the three index paths must give the same bits
+    for leg, fused_gather, dbg in (("two", False, "0"), ("fused", True, "0"), ("generic", True, "16")):
+        os.environ["LNB_FUSED_DBG_LIVE"] = dbg
+        try:
+            for n_rays, over in ((256, {}), (1024, dict(log2_hashmap_size=19, desired_resolution=32768, max_steps=1024))):
+                cfg = check_engine.small_config(fused_gather=fused_gather, perturb=False, **over)
+                if n_rays == 256:
+                    eng, _, _ = check_engine.run_pair(n_rays=n_rays, device=DEV, cfg=cfg, seed=7)
+                else:
+                    eng = _run_engine_only(cfg, n_rays)
+                assert eng.fused_gather == fused_gather
+                n = int(eng.counter[0])
+                assert n > 1000
+                # sample rows in ray order (the march hands out row offsets in arrival order, which differs between runs)
+                rays = eng.rays.cpu().numpy()
+                rays = rays[np.argsort(rays[:, 0])]
+                order = torch.from_numpy(np.concatenate([np.arange(o, o + k) for _, o, k in rays])).to(DEV)
+                assert len(order) == n
+                out[(leg, n_rays)] = dict(enc=eng.enc[order], sigma=eng.sigma[order], rgb=eng.rgb[order],
+                                          sig_out=eng.sig_out[order], fb_s=eng.fb_sigma[:, order],
+                                          fb_h=eng.fb_head[:, order], G=eng.G.clone(), loss=float(eng.loss_acc))
+        finally:
+            os.environ.pop("LNB_FUSED_DBG_LIVE", None)
     for n_rays in (256, 1024):
-        a, b = out[(True, n_rays)], out[(False, n_rays)]
-        for k in ("enc", "sigma", "rgb", "sig_out", "fb_s", "fb_h"):
-            assert torch.equal(a[k], b[k]), (n_rays, k, float((a[k].float() - b[k].float()).abs().max()))
-        assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])      # same per-ray terms, atomic summation order
-        # identical forward -> identical inputs of the backward kernels; only the fp32 atomics' order differs
-        assert float((a["G"] - b["G"]).norm() / b["G"].norm()) < 1e-5
+        for leg in ("fused", "generic"):
+            a, b = out[(leg, n_rays)], out[("two", n_rays)]
+            for k in ("enc", "sigma", "rgb", "sig_out", "fb_s", "fb_h"):
+                assert torch.equal(a[k], b[k]), (leg, n_rays, k, float((a[k].float() - b[k].float()).abs().max()))
+            assert abs(a["loss"] - b["loss"]) <= 1e-6 * abs(b["loss"])      # same per-ray terms, atomic summation order
+            # identical forward -> identical inputs of the backward kernels; only the fp32 atomics' order differs
+            assert float((a["G"] - b["G"]).norm() / b["G"].norm()) < 1e-5
 
 
 def _run_engine_only(cfg, n_rays, seed=11):
