@@ -756,8 +756,10 @@ def profile_kernels(eng, pool, load, iters=5):
     c = eng.cfg
     per_sample_fwd = c.num_levels * 8 * c.level_dim * 2                   # 512 B: L x 2^D corners x F x fp16
     alg = {
-        "lnb_adam_step": ((eng.n_params * 30, "30 B/param: p,g,m,v read (16) + p,m,v write (12) + fp16 shadow (2)") if c.late_grad_zero
-                          else (eng.n_params * 34, "34 B/param: p,g,m,v read (16) + p,m,v,g=0 write (16) + fp16 shadow (2)")),
+        # (data parallel: this rank-0-only pass runs Adam on the rank's 1/world shard, without the exchange)
+        "lnb_adam_step": (((eng.ex.hi - eng.ex.lo) * 30, "30 B/param of this rank's shard: p,g,m,v read (16) + p,m,v write (12) + fp16 shadow (2)")
+                          if c.late_grad_zero else
+                          ((eng.ex.hi - eng.ex.lo) * 34, "34 B/param of this rank's shard: p,g,m,v read (16) + p,m,v,g=0 write (16) + fp16 shadow (2)")),
         "lnb_grid_encode_forward_ex": (rows * (per_sample_fwd + 12 + c.num_levels * c.level_dim * 2),
                                        "SURVEY 8(d): per sample 512 B gathers + 12 B xyz + 64 B features out (the 27 MB "
                                        "table is L2-resident: DRAM traffic is far below this, see `traffic`)"),
