@@ -203,7 +203,10 @@ int lnb_sh_encode_backward(const float *grad, const float *inputs, uint32_t B, u
  * weights = [hidden*in | (num_layers-1)*hidden*hidden | out*hidden] row-major fp16
  * (ffmlp.cu:861-864).  B must be a multiple of 128 (ffmlp.py:254-262 pads).  This build
  * implements hidden_dim == 64, input_dim % 16 == 0 (<= 128), output_dim == 16, activation ReLU
- * (0) and output activation None (6); anything else returns LNB_ERR_UNSUPPORTED.
+ * (0) and output activation None (6); anything else returns LNB_ERR_UNSUPPORTED.  (The
+ * reference's hidden_dim 16 / 32 are served one level up, lidar-nerf_b200/backend.py: the host
+ * pads the weights to 64 hidden units with zeros - exact zeros in every accumulation - and calls
+ * these entry points with hidden_dim = 64.)
  * Accumulation is fp32 in tensor memory (a superset of the reference's fp16 accumulators).
  * forward_buffer / backward_buffer: [num_layers, B, hidden] fp16 (post-activation / d(pre-act)).
  * ---------------------------------------------------------------------------------------- */

@@ -234,12 +234,51 @@ def ffmlp_workspace(device, input_dim, output_dim, hidden_dim, num_layers):
     return ws, need
 
 
+_FFMLP_WIDE = 64          # the hidden width the tensor-core kernels are built for
+_ffmlp_idx = {}
+
+
+def _widen_index(device, input_dim, output_dim, hidden_dim, num_layers):
+    """Positions of a `hidden_dim`-wide network's flat weights ([hidden*in | (L-1)*hidden^2 | out*hidden], ffmlp.cu:861-864)
+    inside the flat weights of the same network zero-padded to 64 hidden units.  The padded units have zero weights in
+    and out: their activations are relu(0) = 0 and contribute exact zeros to every fp32 accumulation, so outputs and
+    gradients are those of the narrow network (the reference's hidden_dim 16 / 32, ffmlp.py:202-210)."""
+    key = (str(device), input_dim, output_dim, hidden_dim, num_layers)
+    idx = _ffmlp_idx.get(key)
+    if idx is None:
+        H, j = _FFMLP_WIDE, torch.arange(hidden_dim)
+        parts = [(j[:, None] * input_dim + torch.arange(input_dim)[None, :]).reshape(-1)]
+        off = H * input_dim
+        for l in range(num_layers - 1):
+            parts.append(off + l * H * H + (j[:, None] * H + j[None, :]).reshape(-1))
+        off += (num_layers - 1) * H * H
+        parts.append(off + (torch.arange(output_dim)[:, None] * H + j[None, :]).reshape(-1))
+        idx = torch.cat(parts).to(device)
+        _ffmlp_idx[key] = idx
+    n_wide = _FFMLP_WIDE * (input_dim + _FFMLP_WIDE * (num_layers - 1) + output_dim)
+    return idx, n_wide
+
+
+def _narrow(hidden_dim):
+    return hidden_dim in (16, 32)
+
+
 class _FFMLP:
-    """ffmlp/src/bindings.cpp:5-10"""
+    """ffmlp/src/bindings.cpp:5-10.  hidden_dim 64 goes straight to the kernels; 16 and 32 run on the same kernels through
+    zero-padded weights (see _widen_index); 128 / 256 are not built (LNB_ERR_UNSUPPORTED -> RuntimeError)."""
 
     @staticmethod
     def ffmlp_forward(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation,
                       output_activation, forward_buffer, outputs):
+        if _narrow(hidden_dim):
+            idx, n_wide = _widen_index(weights.device, input_dim, output_dim, hidden_dim, num_layers)
+            w = torch.zeros(n_wide, dtype=weights.dtype, device=weights.device)
+            w[idx] = weights.reshape(-1)
+            fb = torch.empty(num_layers, B, _FFMLP_WIDE, dtype=forward_buffer.dtype, device=forward_buffer.device)
+            _FFMLP.ffmlp_forward(inputs, w, B, input_dim, output_dim, _FFMLP_WIDE, num_layers, activation,
+                                 output_activation, fb, outputs)
+            forward_buffer.copy_(fb[:, :, :hidden_dim])
+            return
         check(lib.lnb_ffmlp_forward(_hp(inputs, "inputs"), _hp(weights, "weights"), u32(B), u32(input_dim),
                                     u32(output_dim), u32(hidden_dim), u32(num_layers), u32(activation),
                                     u32(output_activation), _hp(forward_buffer, "forward_buffer"),
@@ -248,6 +287,13 @@ class _FFMLP:
     @staticmethod
     def ffmlp_inference(inputs, weights, B, input_dim, output_dim, hidden_dim, num_layers, activation,
                         output_activation, inference_buffer, outputs):
+        if _narrow(hidden_dim):
+            idx, n_wide = _widen_index(weights.device, input_dim, output_dim, hidden_dim, num_layers)
+            w = torch.zeros(n_wide, dtype=weights.dtype, device=weights.device)
+            w[idx] = weights.reshape(-1)
+            _FFMLP.ffmlp_inference(inputs, w, B, input_dim, output_dim, _FFMLP_WIDE, num_layers, activation,
+                                   output_activation, None, outputs)
+            return
         check(lib.lnb_ffmlp_inference(_hp(inputs, "inputs"), _hp(weights, "weights"), u32(B), u32(input_dim),
                                       u32(output_dim), u32(hidden_dim), u32(num_layers), u32(activation),
                                       u32(output_activation), _hp(inference_buffer, "inference_buffer", True),
@@ -256,6 +302,21 @@ class _FFMLP:
     @staticmethod
     def ffmlp_backward(grad, inputs, weights, forward_buffer, B, input_dim, output_dim, hidden_dim, num_layers,
                        activation, output_activation, calc_grad_inputs, backward_buffer, grad_inputs, grad_weights):
+        if _narrow(hidden_dim):
+            idx, n_wide = _widen_index(weights.device, input_dim, output_dim, hidden_dim, num_layers)
+            w = torch.zeros(n_wide, dtype=weights.dtype, device=weights.device)
+            w[idx] = weights.reshape(-1)
+            fb = torch.zeros(num_layers, B, _FFMLP_WIDE, dtype=forward_buffer.dtype, device=forward_buffer.device)
+            fb[:, :, :hidden_dim] = forward_buffer
+            bb = None if backward_buffer is None else torch.zeros_like(fb)
+            gw = None if grad_weights is None else torch.zeros(n_wide, dtype=grad_weights.dtype, device=grad_weights.device)
+            ws = _FFMLP.ffmlp_backward(grad, inputs, w, fb, B, input_dim, output_dim, _FFMLP_WIDE, num_layers, activation,
+                                       output_activation, calc_grad_inputs, bb, grad_inputs, gw)
+            if gw is not None:
+                grad_weights.reshape(-1).copy_(gw[idx])
+            if bb is not None:
+                backward_buffer.copy_(bb[:, :, :hidden_dim])
+            return ws
         ws, need = ffmlp_workspace(grad.device, input_dim, output_dim, hidden_dim, num_layers)
         check(lib.lnb_ffmlp_backward(_hp(grad, "grad"), _hp(inputs, "inputs"), _hp(weights, "weights"),
                                      _hp(forward_buffer, "forward_buffer"), u32(B), u32(input_dim), u32(output_dim),

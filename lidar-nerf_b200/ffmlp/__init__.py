@@ -3,8 +3,9 @@
 Same constructor constraints and flat fp16 weight layout ([hidden*in | (L-1)*hidden^2 | 16*hidden]), same
 initialisation (seed 42, U(+-sqrt(3/hidden)), ffmlp.py:242-245) and the same padding rule (pads
 128 - B % 128 rows even when B % 128 == 0, ffmlp.py:257-262).  The kernels run on the tcgen05 tensor cores with
-fp32 accumulation; this build supports hidden_dim == 64, ReLU, input_dim <= 128 and raises RuntimeError
-otherwise (the reference also supports 16/32/128/256 and other activations).
+fp32 accumulation; this build supports hidden_dim 64 natively and 16 / 32 through zero-padded weights on the same
+kernels (backend._widen_index), ReLU, input_dim <= 128, and raises RuntimeError otherwise (the reference also
+supports 128/256 and other activations).
 """
 import math
 

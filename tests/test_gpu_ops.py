@@ -449,6 +449,48 @@ def test_ffmlp_forward_backward(be, orc, B, ind, nl):
     np.testing.assert_allclose(N_(gw), o_gw, rtol=4e-3, atol=2e-3 * scale)
 
 
+@pytest.mark.parametrize("hidden,ind,nl", [(16, 32, 2), (32, 32, 3), (32, 64, 2)])
+def test_ffmlp_narrow_hidden_widths(be, orc, hidden, ind, nl):
+    """hidden_dim 16 / 32 (ffmlp.py:202-210 of the reference) on the 64-wide tensor-core kernels through zero-padded
+    weights: forward buffer, outputs, input / weight gradients and the backward buffer against the CPU restatement of
+    the NARROW network, with the tolerances of the 64-wide test."""
+    B = 384
+    c = cases.ffmlp_case(60 + hidden, B, ind, hidden, nl, 16)
+    x, w, g = T(c["x"]), T(c["w"]), T(c["g"])
+    fb = torch.empty(nl, B, hidden, device=DEV, dtype=torch.half)
+    out = torch.empty(B, 16, device=DEV, dtype=torch.half)
+    mb = be._ffmlp
+    mb.ffmlp_forward(x, w, B, ind, 16, hidden, nl, 0, 6, fb, out)
+    o_out, o_fb = orc.ffmlp_forward(c["x"], c["w"], ind, 16, hidden, nl)
+    np.testing.assert_allclose(N_(fb), o_fb, rtol=2e-3, atol=2e-3)
+    np.testing.assert_allclose(N_(out), o_out, rtol=2e-3, atol=2e-3)
+    out_inf = torch.empty_like(out)
+    mb.ffmlp_inference(x, w, B, ind, 16, hidden, nl, 0, 6, None, out_inf)
+    assert torch.equal(out, out_inf)
+    gi = torch.zeros(B, ind, device=DEV, dtype=torch.half)
+    gw = torch.zeros_like(w)
+    bb = torch.zeros(nl, B, hidden, device=DEV, dtype=torch.half)
+    mb.ffmlp_backward(g, x, w, fb, B, ind, 16, hidden, nl, 0, 6, True, bb, gi, gw)
+    o_gi, o_gw, o_bb = orc.ffmlp_backward(c["g"], c["x"], c["w"], N_(fb), ind, 16, hidden, nl, True)
+    np.testing.assert_allclose(N_(bb), o_bb, rtol=4e-3, atol=2e-3)
+    np.testing.assert_allclose(N_(gi), o_gi, rtol=4e-3, atol=2e-3)
+    scale = max(1.0, float(np.abs(o_gw).max()))
+    np.testing.assert_allclose(N_(gw), o_gw, rtol=4e-3, atol=2e-3 * scale)
+    # ... and through the reference-shaped module (autograd, 128-row padding rule)
+    from lidar_nerf_b200.ffmlp import FFMLP
+    net = FFMLP(ind, 3, hidden, nl).to(DEV)
+    assert net.weights.numel() == hidden * (ind + hidden * (nl - 1) + 16)
+    xin = torch.rand(200, ind, device=DEV, requires_grad=True)
+    with torch.autocast("cuda", dtype=torch.half):
+        y = net(xin)
+    assert y.shape == (200, 3)
+    y.float().square().sum().backward()
+    o_y, _ = orc.ffmlp_forward(np.concatenate([N_(xin.detach().half()), np.zeros((56, ind), np.float32)]),
+                               N_(net.weights.detach().half()), ind, 16, hidden, nl)
+    np.testing.assert_allclose(N_(y), o_y[:200, :3], rtol=2e-3, atol=2e-3)
+    assert net.weights.grad is not None and float(net.weights.grad.abs().sum()) > 0 and xin.grad is not None
+
+
 def test_ffmlp_rejects_unsupported_shapes(be):
     x = torch.zeros(128, 32, device=DEV, dtype=torch.half)
     w = torch.zeros(64 * (32 + 64 + 16), device=DEV, dtype=torch.half)
@@ -457,7 +499,7 @@ def test_ffmlp_rejects_unsupported_shapes(be):
     with pytest.raises(RuntimeError):
         be._ffmlp.ffmlp_forward(x, w, 100, 32, 16, 64, 2, 0, 6, fb, out)      # B % 128 != 0
     with pytest.raises(RuntimeError):
-        be._ffmlp.ffmlp_forward(x, w, 128, 32, 16, 32, 2, 0, 6, fb, out)      # hidden 32 not built
+        be._ffmlp.ffmlp_forward(x, w, 128, 32, 16, 128, 2, 0, 6, fb, out)     # hidden 128 not built
     with pytest.raises(RuntimeError):
         be._ffmlp.ffmlp_forward(x.float(), w, 128, 32, 16, 64, 2, 0, 6, fb, out)  # dtype
     # an unsupported call must not poison the next (valid) one
