@@ -5,27 +5,31 @@
 // here concurrently inside ONE CTA per SM (832 threads), warp-specialised:
 //
 //   warps  0..15  GATHER     warp <-> level (32 neighbouring samples per gather instruction, the 8 corner rows of TWO
-//                            sample groups = 16 loads per lane in flight), results written as fp16 pairs STRAIGHT INTO
-//                            the swizzled shared-memory operand tile of the first MLP layer (a ring of kStages tiles,
-//                            full/empty mbarriers; coordinates double-buffered in shared memory);
+//                            sample groups = 16 loads per lane in flight; dense / power-of-two-hash / generic indexing
+//                            chosen once per level, not per corner), results written as fp16 pairs STRAIGHT INTO the
+//                            swizzled shared-memory operand tile of the first MLP layer (a ring of kStages tiles,
+//                            full/empty mbarriers).  Sample positions arrive through a TMA ring (cp.async.bulk of
+//                            1.5 KB per tile onto an mbarrier, two tiles ahead): no CTA-wide barrier in the tile loop;
 //   warps 16..23  EPILOGUE   two groups of 128 threads (thread = tile row = TMEM lane), one 128-row tile in flight each:
-//                            tcgen05.ld accumulator row, 32 columns at a time -> (+per-ray bias) -> ReLU -> fp16 ->
-//                            operand tile of the next layer; the saved activations leave the SM as warp-local coalesced
-//                            512-byte stores read back from that tile while the tensor core works; sigma = exp(h0),
-//                            geo features -> head operand; sigmoid -> (ray-drop, intensity); one mbarrier arrival per
-//                            WARP (fence.proxy.async by every lane, __syncwarp, lane 0 arrives);
+//                            tcgen05.ld accumulator row, 16 columns per load with three loads in flight -> (+per-ray
+//                            bias) -> ReLU -> fp16 -> operand tile of the next layer; the saved activations leave the SM
+//                            through TMA tensor stores (cp.async.bulk.tensor.2d of each warp's 32 rows, un-swizzled by
+//                            the copy engine) while the tensor core works; sigma = exp(h0), geo features -> head
+//                            operand; sigmoid -> (ray-drop, intensity); one mbarrier arrival per WARP
+//                            (fence.proxy.async by every lane, __syncwarp, lane 0 arrives);
 //   warps 24..25  MMA        one warp per tile slot; an elected lane issues the slot's tcgen05.mma chain (M128 x N64/N16 x
 //                            K16, fp32 accumulators in tensor memory, 128 columns per slot) in program order behind
-//                            blocking mbarrier waits, descriptors in uniform registers.
+//                            blocking mbarrier waits.
 //
 // MLP weights are staged ONCE per CTA by the TMA engine: `lnb_field_pack_weights` lays the six weight tiles out in global
 // memory as the exact shared-memory image (128-byte rows, 16-byte chunks xor-swizzled) and the kernel pulls that image
 // with cp.async.bulk (SASS UBLKCP) onto an mbarrier - no per-thread LDGSTS, no register staging.
 //
 // Numerics are those of k_grid_fwd + k_field_fwd (same helpers, same rounding points): tests compare the two paths
-// bit-for-bit on everything the step keeps.  Measured (profiles/r02_fused_forward_diag.txt): at 385 k samples 164 us vs
-// 97 + 72 us for the two kernels - the overlap is real but each role only has a share of the SM's warps and registers
-// (gather alone 136 us with 16 warps vs 97 us with 48; MLP alone 99 us vs 72 us), so the gain over the sequence is small.
+// bit-for-bit on everything the step keeps, with every level forced through the generic indexing path as a third leg.
+// Measured (profiles/r02_fused_forward_diag.txt, r02_fused_forward_timeline.txt): at 385 k samples 150 us vs 97 + 72 us
+// for the two kernels; gather alone 109 us, MLP alone 80 us - the two halves compete for the LSU / L1 / L2 path (the saved
+// activations cost 28 us of L2 bandwidth the gather would otherwise have), which is what is left between 150 and 109.
 //
 // Reference behaviour: gridencoder.cu:95-199 (gather), ffmlp.cu:460-576 (MLP), network.py:162-237 (wiring).
 #include <cuda.h>
@@ -41,7 +45,6 @@ namespace lnb {
 namespace {
 
 constexpr uint32_t kGatherWarps = 16;
-constexpr uint32_t kGatherThreads = kGatherWarps * 32;
 constexpr uint32_t kGroups = 2;                        // epilogue groups (128 threads, thread = tile row)
 // Measured on B200 (385 k samples, profiles/r02_fused_forward_diag.txt): one tile per epilogue group (2 tiles in flight)
 // 164 us, two per group (4 in flight) 181 us - the extra tiles in flight only lengthen the gather's wait for a free stage.
@@ -53,7 +56,6 @@ constexpr uint32_t kGroups = 2;                        // epilogue groups (128 t
 #endif
 constexpr uint32_t kSlotsPerGroup = LNB_FUSED_SLOTS_PER_GROUP;   // tiles a group keeps in flight, processed phase by phase in turn
 constexpr uint32_t kSlots = kGroups * kSlotsPerGroup;  // tiles in flight in the MLP part of one CTA
-constexpr uint32_t kGroupThreads = 128;
 constexpr uint32_t kEpiWarp0 = kGatherWarps;           // first epilogue warp (multiple of 4: TMEM lane quadrants)
 constexpr uint32_t kMmaWarpIdx = kEpiWarp0 + kGroups * 4;
 constexpr uint32_t kFusedThreads = (kMmaWarpIdx + kSlots) * 32;      // 832: one MMA warp per tile slot
@@ -133,9 +135,6 @@ __device__ __forceinline__ void tma_store_rows(const CUtensorMap *tm, uint32_t s
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
-__device__ __forceinline__ void named_bar(uint32_t id, uint32_t n) {
-    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory");
-}
 // -----------------------------------------------------------------------------------------------------
 // weight image: [Ws_in | Ws_hid x n | Ws_out (2 KB) | Wh_geo | Wh_hid x n | Wh_out (2 KB)], every tile in the
 // one operand layout of tcgen05.cuh (tile_chunk_addr).  Chunks that hold no weight stay zero (the image is cleared
@@ -271,11 +270,7 @@ k_field_fused_fwd(const FusedArgs a, const __grid_constant__ CUtensorMap tm_fb_s
             mbar_init(bar_xempty + 8 * s, 1 + 4);                 // tcgen05.commit + one arrival per epilogue warp
         }
         for (uint32_t q = 0; q < kSlots; ++q) {
-#ifdef LNB_FUSED_THREAD_ARRIVE
-            mbar_init(bar_ready + 8 * q, kGroupThreads);
-#else
             mbar_init(bar_ready + 8 * q, 4);                      // one arrival per epilogue warp of the owning group
-#endif
             mbar_init(bar_done + 8 * q, 1);
         }
         mbar_init(bar_w, 1);
@@ -487,14 +482,6 @@ k_field_fused_fwd(const FusedArgs a, const __grid_constant__ CUtensorMap tm_fb_s
                 *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * cpr + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
             }
         };
-#ifdef LNB_FUSED_THREAD_ARRIVE
-        auto publish = [&](uint32_t bar) {
-            fence_proxy_async();
-            fence_before_sync();
-            mbar_arrive(bar);
-        };
-        auto arrive_warp = [&](uint32_t bar) { mbar_arrive(bar); };
-#else
         auto publish = [&](uint32_t bar) {                  // this warp's rows of an operand tile are in place
             fence_proxy_async();
             fence_before_sync();
@@ -505,7 +492,6 @@ k_field_fused_fwd(const FusedArgs a, const __grid_constant__ CUtensorMap tm_fb_s
             __syncwarp();
             if (lane == 0) mbar_arrive(bar);
         };
-#endif
 
         for (uint32_t q = 0; q < kSlotsPerGroup; ++q)       // tensor memory of the group's slots is free
             if (g * kSlotsPerGroup + q < n_my) arrive_warp(bar_ready + 8 * (g * kSlotsPerGroup + q));

@@ -216,3 +216,31 @@ def test_network_tcnn_module_path_without_tinycudann():
         for k, v in saved.items():
             if v is not None:
                 sys.modules[k] = v
+
+
+def test_ffmlp_narrow_width_padding_map_reproduces_the_narrow_network():
+    """backend._widen_index: the flat weights of a hidden_dim 16 / 32 FFMLP scattered into the flat weights of the same
+    network with 64 hidden units (zeros elsewhere) give bit-identical outputs, forward buffers, input gradients and
+    weight gradients in the CPU restatement - the property the GPU path for those widths relies on."""
+    import numpy as np
+    import torch
+    from oracle import oracle as orc
+    from lidar_nerf_b200.backend import _widen_index
+    import cases
+    for hidden, ind, nl in ((16, 32, 2), (32, 48, 3)):
+        c = cases.ffmlp_case(7 + hidden, 128, ind, hidden, nl, 16)
+        idx, n_wide = _widen_index(torch.device("cpu"), ind, 16, hidden, nl)
+        assert idx.numel() == c["w"].size and n_wide == 64 * (ind + 64 * (nl - 1) + 16)
+        assert idx.unique().numel() == idx.numel()
+        wide = np.zeros(n_wide, np.float16)
+        wide[idx.numpy()] = c["w"]
+        out_n, fb_n = orc.ffmlp_forward(c["x"], c["w"], ind, 16, hidden, nl)
+        out_w, fb_w = orc.ffmlp_forward(c["x"], wide, ind, 16, 64, nl)
+        assert np.array_equal(out_n, out_w) and np.array_equal(fb_n, fb_w[:, :, :hidden])
+        assert not fb_w[:, :, hidden:].any()
+        gi_n, gw_n, bb_n = orc.ffmlp_backward(c["g"], c["x"], c["w"], fb_n, ind, 16, hidden, nl, True)
+        gi_w, gw_w, bb_w = orc.ffmlp_backward(c["g"], c["x"], wide, fb_w, ind, 16, 64, nl, True)
+        assert np.array_equal(gi_n, gi_w) and np.array_equal(gw_n, gw_w[idx.numpy()]) and np.array_equal(bb_n, bb_w[:, :, :hidden])
+        rest = np.ones(n_wide, bool)
+        rest[idx.numpy()] = False
+        assert not gw_w[rest].any()
