@@ -251,6 +251,8 @@ def main():
     cfg = FieldConfig(**wl["field"])
     if os.environ.get("LNB_FUSED_GATHER") == "0":         # A/B switch: two-kernel forward instead of the persistent kernel
         cfg.fused_gather = False
+    if os.environ.get("LNB_L2_PERSIST") == "0":           # A/B switch: no access-policy window on the hash table
+        cfg.l2_persist_table = False
     if os.environ.get("LNB_COMPACT_BACKWARD") == "0":     # A/B switch for the diagnostics in profiles/
         cfg.compact_backward = False
     if os.environ.get("LNB_LATE_GRAD_ZERO") == "0":

@@ -398,6 +398,12 @@ int lnb_field_forward(const void *enc, const void *w_sigma, const void *w_head, 
                       uint32_t head_in_pad, uint32_t head_layers, uint32_t degree, uint32_t hidden,
                       float density_scale, void *fb_sigma, void *sig_out, float *sigma, void *fb_head, float *rgb,
                       const int32_t *n_active, lnb_stream_t stream);
+/* L2 residency of the hash table for the persistent forward kernel: declares [table, table + bytes) as the table later
+ * lnb_field_fused_forward*() launches read; reserves persisting L2 for it and makes those launches carry an access-policy
+ * window (table lines persisting, everything else streaming).  bytes = 0 switches it off.  Process-wide setting.
+ * (No counterpart in the reference: its gather, gridencoder.cu:95-199, leaves residency to the hardware.) */
+int lnb_field_set_l2_window(const void *table, size_t bytes);
+
 /* ------------------------------------------------------------------------------------------
  * ONE persistent kernel per ray packet: lnb_grid_encode_forward_ex + lnb_field_forward in a single launch
  * (north star of this library; replaces gridencoder.cu:95-199 + ffmlp.cu:460-576 x 2 + the torch glue of

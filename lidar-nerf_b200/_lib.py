@@ -51,7 +51,7 @@ SYMBOLS = [
     "lnb_chamfer_forward", "lnb_chamfer_backward", "lnb_lidar_to_pano_workspace_bytes", "lnb_lidar_to_pano",
     "lnb_pano_to_lidar_workspace_bytes", "lnb_pano_to_lidar",
     "lnb_field_head_backward_rows", "lnb_ffmlp_backward_accumulate_rows", "lnb_grid_encode_backward_rows",
-    "lnb_field_fused_weight_bytes", "lnb_field_pack_weights", "lnb_field_fused_forward",
+    "lnb_field_fused_weight_bytes", "lnb_field_pack_weights", "lnb_field_fused_forward", "lnb_field_set_l2_window",
     "lnb_lidar_loss_ex", "lnb_lidar_composite_forward", "lnb_lidar_composite_backward", "lnb_dp_adam_exchange_mc", "lnb_lidar_batch", "lnb_packbits_dev",
     "lnb_field_supported_bf16", "lnb_field_ray_terms_bf16", "lnb_field_forward_bf16", "lnb_field_head_backward_bf16", "lnb_field_head_backward_rows_bf16", "lnb_field_fused_weight_bytes_bf16", "lnb_field_pack_weights_bf16", "lnb_field_fused_forward_bf16", "lnb_ffmlp_forward_ex_bf16", "lnb_ffmlp_inference_bf16", "lnb_ffmlp_backward_accumulate_bf16", "lnb_ffmlp_backward_accumulate_rows_bf16",
 ]

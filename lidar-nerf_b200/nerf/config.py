@@ -55,6 +55,7 @@ class FieldConfig:
     fused_field: bool = True             # density MLP + LiDAR head as the fused field kernels (csrc/field.cu)
     fused_gather: bool = True            # hash-grid gather + density MLP + LiDAR head forward as ONE persistent kernel
                                          # (csrc/field_fused.cu); needs fused_field
+    l2_persist_table: bool = True        # persistent forward kernel: access-policy window keeping the fp16 table in L2
     fused_composite: bool = True         # composite fwd + LiDAR loss + composite bwd as one kernel (csrc/raymarching.cu)
     compact_backward: bool = True        # backward kernels walk only the samples up to each ray's early stop
     late_grad_zero: bool = True          # zero the gradient table right before the scatter (L2-resident) instead of in Adam

@@ -184,6 +184,12 @@ class LidarFieldEngine:
             raise RuntimeError("mlp_dtype='bf16' needs the persistent forward kernel (fused_field and fused_gather, "
                                "level_dim 2): the stand-alone grid encoder writes fp16 features")
         self.wimage = torch.zeros(max(wbytes, 16), dtype=torch.uint8, device=dev) if self.fused_gather else None
+        if self.fused_gather and c.l2_persist_table:
+            # keep the fp16 table (27 MB at T = 2^19) resident in L2 across the step's streaming kernels
+            lib.lnb_field_set_l2_window.argtypes = [C.c_void_p, C.c_size_t]
+            rc = lib.lnb_field_set_l2_window(vp(self.table_h.data_ptr()), sz(self.n_table * 2))
+            if rc not in (0, -2):            # LNB_ERR_UNSUPPORTED: no persisting L2 on this device - run without
+                _ck(rc, "field_set_l2_window")
         self.ray_enc = torch.zeros(N, c.head_in_dim, dtype=self.mlp_torch_dtype, device=dev)
         self.ray_bias = torch.zeros(N, c.hidden_dim, **f)
 

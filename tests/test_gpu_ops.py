@@ -448,6 +448,30 @@ def test_ffmlp_forward_backward(be, orc, B, ind, nl):
     scale = max(1.0, float(np.abs(o_gw).max()))
     np.testing.assert_allclose(N_(gw), o_gw, rtol=4e-3, atol=2e-3 * scale)
 
+    # live against the UNMODIFIED reference kernels (oracle/_ref/_ffmlp; wmma with fp16 accumulators + split-K CUTLASS
+    # GEMMs, ffmlp.cu:460-733,1059-1264): same tensors in, relative Frobenius error of every output
+    ref = refcuda.load("_ffmlp")
+    if ref is not None:
+        def rel(a, b):
+            return float((a.float() - b.float()).norm() / b.float().norm().clamp_min(1e-12))
+        r_fb, r_out = torch.empty_like(fb), torch.empty_like(out)
+        ref.ffmlp_forward(x, w, B, ind, 16, 64, nl, 0, 6, r_fb, r_out)
+        torch.cuda.synchronize()
+        obs = {"fb": rel(fb, r_fb), "out": rel(out, r_out)}
+        ref.allocate_splitk(nl + 1)
+        r_gi = torch.zeros(B, ind, device=DEV, dtype=torch.half)
+        r_gw = torch.zeros_like(w)
+        r_bb = torch.zeros(nl, B, 64, device=DEV, dtype=torch.half)
+        ref.ffmlp_backward(g, x, w, r_fb, B, ind, 16, 64, nl, 0, 6, True, r_bb, r_gi, r_gw)
+        torch.cuda.synchronize()
+        obs.update(gi=rel(gi, r_gi), gw=rel(gw, r_gw))
+        ref.free_splitk()
+        from conftest import record_parity
+        record_parity(f"ffmlp_vs_reference_cuda[{B},{ind},{nl}]", **obs)
+        # forward: both round every layer to fp16 (observed 3e-4 / 6e-4).  backward: the reference accumulates dgrad and
+        # the split-K wgrad in fp16, this library (like the CPU restatement, 4e-3 above) in fp32 - observed 2.7e-2 / 1.6e-2
+        assert obs["fb"] < 5e-3 and obs["out"] < 1e-2 and obs["gi"] < 0.1 and obs["gw"] < 0.1, obs
+
 
 @pytest.mark.parametrize("hidden,ind,nl", [(16, 32, 2), (32, 32, 3), (32, 64, 2)])
 def test_ffmlp_narrow_hidden_widths(be, orc, hidden, ind, nl):
