@@ -448,6 +448,8 @@ class LidarFieldEngine:
                                                        p(self.g_enc), p(self.g_sigma_w), li, nl, s),
                 "ffmlp_bwd_rows(sigma)")
             if c.late_grad_zero:
+                # (Measured and rejected: clearing the table on a forked branch UNDER the density-MLP backward hides the
+                # 10 us memset but costs 20 us - the zeroed lines must be the last thing that entered L2 before the scatter.)
                 self.g_table.zero_()
             _ck(lib.lnb_grid_encode_backward_rows(p(self.g_enc), p(self.xyzs), p(self.table_h), p(self.offsets),
                                                   p(self.g_table), u32(M), u32(3), u32(c.level_dim), u32(c.num_levels),
