@@ -487,6 +487,14 @@ k_field_fused_fwd(const FusedArgs a, const __grid_constant__ CUtensorMap tm_fb_s
                 }
                 return;
             }
+            if (cpr == 4) {                                  // 32-wide rows (L16 x F2 features): 4 copies, no division
+#pragma unroll
+                for (uint32_t j = 0; j < 4; ++j) {
+                    const uint32_t q = lane + 32 * j, rr = wq * 32u + (q >> 2), c = q & 3u;
+                    *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * 4 + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
+                }
+                return;
+            }
             for (uint32_t q = lane; q < 32 * cpr; q += 32) {
                 const uint32_t rr = wq * 32u + q / cpr, c = q % cpr;
                 *reinterpret_cast<uint4 *>(dst_row0 + ((size_t)rr * cpr + c) * 8) = lds128(tile_chunk_addr(tile, rr, c));
