@@ -811,7 +811,12 @@ int lnb_field_fused_forward(const float *xyzs, const void *table, const int32_t 
     FusedShape fs;
     int rc = make_fused_shape(L * C, sigma_layers, head_in_pad, head_layers, degree, hidden, &fs);
     if (rc != LNB_OK) return rc;
-    const size_t smem = fused_smem_bytes(fs);
+    size_t smem = fused_smem_bytes(fs);
+    {   // diagnostics only: LNB_FUSED_EXTRA_SMEM_KB pads the request (how much does the gather depend on the L1 share of the
+        // 256 KB array?  profiles/r02_fused_forward_diag.txt)
+        static const size_t extra = [] { const char *e = getenv("LNB_FUSED_EXTRA_SMEM_KB"); return e ? (size_t)atoi(e) * 1024 : (size_t)0; }();
+        smem += extra;
+    }
     if (smem > 226 * 1024) return LNB_ERR_UNSUPPORTED;
     if (M == 0) return LNB_OK;
     cudaError_t e = cudaFuncSetAttribute(k_field_fused_fwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
