@@ -347,10 +347,21 @@ def main():
             losses.append(eng.read_loss_last())
 
     def spin(seconds):
-        """Untimed steps at load: GPU clocks, caches and the allocator are in steady state when the timed blocks begin."""
-        t_end = time.perf_counter() + seconds
+        """Untimed steps at load: GPU clocks, caches and the allocator are in steady state when the timed blocks begin.
+        Data parallel: every step is a collective, so all ranks MUST run the same number of steps - the decision to go on
+        is taken together (all-reduce MIN of each rank's own clock test; a rank-local `while clock < t_end` let one rank
+        run one 16-step chunk more than the others and wait for partners that never came)."""
+        skew = float(os.environ.get("LNB_BENCH_SPIN_SKEW_MS", "0")) * 1e-3 * rank      # (test hook: ranks disagree on purpose)
+        t_end = time.perf_counter() + seconds + skew
         n = 0
-        while time.perf_counter() < t_end:
+        while True:
+            go = time.perf_counter() < t_end
+            if world > 1:
+                flag = torch.tensor([1 if go else 0], device=dev, dtype=torch.int32)
+                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+                go = bool(int(flag.item()))
+            if not go:
+                break
             run(16, False)
             torch.cuda.synchronize()
             n += 16
