@@ -238,6 +238,7 @@ def main():
     import torch.distributed as dist
     from lidar_nerf_b200 import _lib
     from lidar_nerf_b200.nerf.engine import LidarFieldEngine, FieldConfig
+    from lidar_nerf_b200.nerf import dp
     from lidar_nerf_b200.data.synthetic import SyntheticLidarSequence
 
     torch.cuda.set_device(local)
@@ -355,12 +356,7 @@ def main():
         t_end = time.perf_counter() + seconds + skew
         n = 0
         while True:
-            go = time.perf_counter() < t_end
-            if world > 1:
-                flag = torch.tensor([1 if go else 0], device=dev, dtype=torch.int32)
-                dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-                go = bool(int(flag.item()))
-            if not go:
+            if not dp.all_ranks_agree(time.perf_counter() < t_end, dev):
                 break
             run(16, False)
             torch.cuda.synchronize()

@@ -77,3 +77,16 @@ class ShardedExchange:
         else:
             dist.all_gather_into_tensor(full_padded, shard)
         return full_padded
+
+
+def all_ranks_agree(go, device=None):
+    """True only if EVERY rank passes True (all-reduce MIN; identity on one rank).  For loops whose exit test is rank-local
+    (a wall-clock budget, a data-dependent stop) but whose body contains collectives: every rank must leave the loop in
+    the same iteration, or the ranks that go on wait for partners that never come."""
+    if not is_distributed():
+        return bool(go)
+    import torch
+    flag = torch.tensor([1 if go else 0], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    return bool(int(flag.item()))
+

@@ -129,6 +129,15 @@ def _dp_worker(rank, world, port, out):
     got = torch.zeros(ex.n_padded, dtype=torch.float16)
     ex.all_gather(got, p_shard)
     assert torch.equal(got, want)
+    # loops with collectives inside and a rank-local exit test: nobody goes on unless everybody does
+    assert dp.all_ranks_agree(True) is True
+    assert dp.all_ranks_agree(rank == 0) is False
+    assert dp.all_ranks_agree(False) is False
+    steps = 0
+    while dp.all_ranks_agree(steps < 3 + 2 * rank):         # rank 1 would like two more iterations
+        dp.allreduce_gradient_(torch.ones(4))               # (the collective a mismatched loop would hang in)
+        steps += 1
+    assert steps == 3
     if rank == 0:
         out.put("ok")
     dist.destroy_process_group()
