@@ -67,6 +67,55 @@ class NeRFNetwork(NeRFRenderer):
             raise NotImplementedError("bg_radius > 0 (background model) is not implemented in lidar-nerf_b200; the LiDAR "
                                       "branch does not use it - pass bg_radius <= 0")
 
+    # ------------------------------------------------------------------------------------------------------------
+    # checkpoints of the reference's network.py (bias-free nn.Linear stacks: `sigma_net.{i}.weight`, ...)
+    # ------------------------------------------------------------------------------------------------------------
+    @staticmethod
+    def linear_stack_to_ffmlp(weights, input_dim_padded, hidden_dim, ffmlp_layers, padded_output_dim=16):
+        """[W_0 (hidden x in), ..., W_last (out x hidden)] of a bias-free ReLU nn.Linear stack -> the flat FFMLP weight
+        vector [hidden*in | (L-1)*hidden^2 | 16*hidden] (ffmlp.cu:861-864) of an FFMLP with `ffmlp_layers` layers computing
+        the SAME function: input columns / output rows are zero-padded, and where the FFMLP has more matmuls than the stack
+        (the reference's two-Linear density net vs the smallest FFMLP, three matmuls) identity layers are inserted behind
+        the first ReLU - relu(I relu(h)) = relu(h) exactly, also in fp16."""
+        weights = [torch.as_tensor(w, dtype=torch.float32) for w in weights]
+        n_mat = ffmlp_layers + 1
+        if len(weights) > n_mat or len(weights) < 2:
+            raise ValueError(f"a stack of {len(weights)} Linear layers does not fit an FFMLP with {ffmlp_layers} layers")
+        w_in, w_out, mids = weights[0], weights[-1], weights[1:-1]
+        if w_in.shape[0] != hidden_dim or w_out.shape[1] != hidden_dim or w_in.shape[1] > input_dim_padded or \
+                w_out.shape[0] > padded_output_dim or any(tuple(m.shape) != (hidden_dim, hidden_dim) for m in mids):
+            raise ValueError("layer shapes do not match the FFMLP")
+        eye = torch.eye(hidden_dim)
+        mids = [eye] * (n_mat - 2 - len(mids)) + mids
+        flat = [F.pad(w_in, (0, input_dim_padded - w_in.shape[1])).reshape(-1)]
+        flat += [m.reshape(-1) for m in mids]
+        flat.append(F.pad(w_out, (0, 0, 0, padded_output_dim - w_out.shape[0])).reshape(-1))
+        return torch.cat(flat)
+
+    def load_reference_state_dict(self, state_dict, strict=True):
+        """Load a checkpoint of the reference's `NeRFNetwork` (lidarnerf/nerf/network.py: `encoder.embeddings`,
+        `sigma_net.{i}.weight`, `color_net.{i}.weight`, `lidar_color_net.{i}.weight`, renderer buffers).  With
+        use_ffmlp=False the keys coincide and this is load_state_dict; with the fused MLPs the Linear stacks are converted
+        (linear_stack_to_ffmlp).  Checkpoints of network_tcnn.py hold tiny-cuda-nn's private parameter layout and cannot
+        be converted."""
+        sd = dict(state_dict.get("model", state_dict))
+        if any(k.endswith(".params") for k in sd):
+            raise ValueError("tiny-cuda-nn checkpoint (network_tcnn.py): its parameter layout is private to tcnn")
+        if not self.use_ffmlp:
+            return self.load_state_dict(sd, strict=strict)
+        out = {}
+        for name, net, pad_in in (("sigma_net", self.sigma_net, self.pad_in), ("color_net", self.color_net, self.pad_rgb),
+                                  ("lidar_color_net", self.lidar_color_net, self.pad_lidar)):
+            ws, i = [], 0
+            while f"{name}.{i}.weight" in sd:
+                ws.append(sd.pop(f"{name}.{i}.weight"))
+                i += 1
+            if ws:
+                out[f"{name}.weights"] = self.linear_stack_to_ffmlp(ws, pad_in, net.hidden_dim, net.num_layers,
+                                                                    net.padded_output_dim)
+        out.update(sd)
+        return self.load_state_dict(out, strict=strict)
+
     def fused_unsupported_reason(self):
         from .fused_render import FusedLidarRender
         return FusedLidarRender.supported(self)

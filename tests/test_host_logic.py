@@ -253,3 +253,51 @@ def test_ffmlp_narrow_width_padding_map_reproduces_the_narrow_network():
         rest = np.ones(n_wide, bool)
         rest[idx.numpy()] = False
         assert not gw_w[rest].any()
+
+
+def test_reference_linear_stack_checkpoint_maps_onto_the_ffmlp_layout():
+    """NeRFNetwork.linear_stack_to_ffmlp: the reference's bias-free nn.Linear stacks (network.py:45-98) as flat FFMLP
+    weights computing the same function - the two-Linear density net needs an identity layer (an FFMLP has >= 3 matmuls),
+    the three-Linear LiDAR head maps one to one.  Checked through the CPU restatement of the FFMLP against the plain
+    matrix products with fp16-rounded activations."""
+    from oracle import oracle as orc
+    from lidar_nerf_b200.nerf.network import NeRFNetwork
+    rng = np.random.default_rng(5)
+    h16 = lambda a: a.astype(np.float16).astype(np.float32)   # noqa: E731
+
+    def stack(x, ws):
+        h = h16(x)
+        for i, w in enumerate(ws):
+            h = h16(h @ h16(w).T)
+            if i + 1 < len(ws):
+                h = np.maximum(h, 0)
+        return h
+
+    for in_dim, pad_in, out_dim, n_lin, ff_layers in ((32, 32, 16, 2, 2), (39, 48, 2, 3, 2), (39, 48, 2, 3, 3)):
+        dims = [in_dim] + [64] * (n_lin - 1) + [out_dim]
+        ws = [rng.uniform(-0.3, 0.3, size=(b, a)).astype(np.float32) for a, b in zip(dims[:-1], dims[1:])]
+        flat = NeRFNetwork.linear_stack_to_ffmlp(ws, pad_in, 64, ff_layers).numpy()
+        assert flat.size == 64 * (pad_in + 64 * (ff_layers - 1) + 16)
+        x = rng.uniform(-1, 1, size=(128, in_dim)).astype(np.float32)
+        xp = np.pad(x, ((0, 0), (0, pad_in - in_dim)))
+        got, _ = orc.ffmlp_forward(xp, flat, pad_in, 16, 64, ff_layers)
+        np.testing.assert_allclose(got[:, :out_dim], stack(x, ws), rtol=2e-3, atol=2e-3)
+        assert not got[:, out_dim:].any()
+    with pytest.raises(ValueError):
+        NeRFNetwork.linear_stack_to_ffmlp([np.zeros((64, 32), np.float32)] * 5, 32, 64, 2)
+    # ... and through the module: a reference-shaped state_dict lands in the three flat FFMLP parameters
+    net = NeRFNetwork(encoding="frequency", multires=5, use_ffmlp=True)
+    g = torch.Generator().manual_seed(0)
+    sd = {"sigma_net.0.weight": torch.randn(64, net.in_dim, generator=g), "sigma_net.1.weight": torch.randn(16, 64, generator=g)}
+    for name, in_dim, out in (("color_net", net.in_dim_dir + 15, 3), ("lidar_color_net", net.in_dim_lidar_dir + 15, 2)):
+        sd.update({f"{name}.0.weight": torch.randn(64, in_dim, generator=g), f"{name}.1.weight": torch.randn(64, 64, generator=g),
+                   f"{name}.2.weight": torch.randn(out, 64, generator=g)})
+    net.load_reference_state_dict(sd, strict=False)
+    w = net.sigma_net.weights.detach()
+    assert torch.equal(w[:64 * net.pad_in].reshape(64, net.pad_in)[:, :net.in_dim], sd["sigma_net.0.weight"])
+    assert torch.equal(w[64 * net.pad_in:64 * net.pad_in + 64 * 64].reshape(64, 64), torch.eye(64))       # inserted identity
+    assert torch.equal(w[-16 * 64:].reshape(16, 64), sd["sigma_net.1.weight"])
+    wl = net.lidar_color_net.weights.detach()
+    assert torch.equal(wl[-16 * 64:].reshape(16, 64)[:2], sd["lidar_color_net.2.weight"]) and not wl[-16 * 64:].reshape(16, 64)[2:].any()
+    with pytest.raises(ValueError):
+        net.load_reference_state_dict({"sigma_net.params": torch.zeros(4)})
