@@ -179,6 +179,25 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert "workload" in d["config"]
 
 
+def test_bench_reference_arm_names_the_product_config_and_never_maps_the_product_library():
+    """The two arms must describe the SAME workload (`config` identical), and the reference arm must not load
+    liblnb200.so - the driver records which native libraries each arm mapped."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = ("import sys, json; sys.argv = ['bench.py', '--impl', 'reference', '--steps', '1', '--warmup', '1', '--cpu-rays', '32'];"
+            "import bench; rc = bench.main(); maps = open('/proc/self/maps').read();"
+            "print('MAPS', json.dumps({'lnb': 'liblnb200' in maps, 'oracle': 'lnb_oracle' in maps or 'oracle' in maps, 'rc': rc,"
+            " 'cfg': bench.bench_config(2)}))")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][0])
+    info = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("MAPS ")][0][5:])
+    assert info["rc"] in (0, None) and info["lnb"] is False and info["oracle"] is True
+    assert line["config"] == info["cfg"]
+
+
 @pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-GPU behaviour")
 def test_bench_product_arm_fails_loudly_without_a_gpu():
     """No CPU fallback: the product arm must not print a result line when there is no CUDA device."""
